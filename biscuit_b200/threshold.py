@@ -1,0 +1,492 @@
+"""UQ thresholding on the GPU -- drop-in for reference `biscuit.threshold`.
+
+Same call surface, argument meaning, DataFrame mutation and error behaviour as reference
+biscuit/threshold.py (`process_tile_predictions` 125-177, `process_group_predictions` 180-245,
+`apply` 248-361, `detect` 364-475, `from_cv` 478-557); the arithmetic runs in
+libbiscuit_b200.so (csrc/threshold.cu) through the C ABI of include/biscuit_b200.h:
+
+    tile pass              -> bq_tile_process      (error / correct / incorrect / y_pred_bin)
+    groupby(level).mean()  -> bq_group_reduce      (row-order Kahan sum in the column dtype)
+    roc_curve + Youden + auc -> bq_tile_roc / bq_roc (radix sort + scan, fp64 J, first argmax)
+    slide filter + confusion -> bq_group_apply
+
+This module only factorises the string keys, resolves NumPy's scalar-promotion rule for each
+comparison and rebuilds the DataFrames.  There is no CPU fallback: without the CUDA library and
+a B200 every function raises `NativeLibraryError`.
+
+Deliberate differences from the reference (all documented in DESIGN.md):
+  * plotting (`plot=True`) is out of scope and ignored with a warning;
+  * ROC curves whose result the reference discards (tile ROC when `tile_pred` is numeric, the
+    group ROC when `slide_pred` is numeric) are not computed;
+  * a missing y_true / y_pred / uncertainty column raises ValueError (the reference raises
+    UnboundLocalError from a bug at threshold.py:184-186).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from . import _ffi, errors
+
+log = logging.getLogger("biscuit_b200")
+
+_FLOAT_TYPES = (float, np.float16, np.float32, np.float64)   # threshold.py:411
+_THRESH_KEYS = ("tile_uq", "slide_uq", "tile_pred", "slide_pred")
+_RESULT_KEYS = ("auc", "percent_incl", "acc", "sensitivity", "specificity")
+
+
+def _is_detect(x) -> bool:
+    return isinstance(x, str) and x == "detect"
+
+
+def _cmp_scalar(t, col_dtype) -> float:
+    """The float64 value a column of `col_dtype` is effectively compared with under NumPy >= 2
+    promotion (NEP 50), which pandas follows: python scalars are weak (rounded to the column
+    dtype first), NumPy scalars are strong (float32 column vs np.float64 compares in float64)."""
+    if isinstance(t, (np.floating, np.integer, np.bool_)) or (isinstance(t, np.ndarray) and t.ndim == 0):
+        return float(t)
+    if col_dtype == np.float32:
+        with np.errstate(over="ignore"):
+            return float(np.float32(t))
+    return float(t)
+
+
+def _float_col(a: np.ndarray) -> np.ndarray:
+    if a.dtype == np.float32 or a.dtype == np.float64:
+        return np.ascontiguousarray(a)
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _label_col(a: np.ndarray, what="y_true") -> np.ndarray:
+    """uint8 labels; anything sklearn's roc_curve would reject (non-binary, NaN) -> ValueError."""
+    if a.dtype == np.bool_:
+        return np.ascontiguousarray(a, dtype=np.uint8)
+    with np.errstate(invalid="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = a.astype(np.uint8)
+    if not np.array_equal(b, a):
+        raise ValueError(f"{what}: labels must be 0/1 (continuous / multiclass format is not supported)")
+    return np.ascontiguousarray(b)
+
+
+def _roc_struct():
+    return _ffi.RocResult()
+
+
+class _DeviceTable:
+    """One tile table resident on the GPU (bq_table) for the duration of a call."""
+
+    def __init__(self, y_pred, uncertainty, y_true, ctx=None):
+        self.ctx = ctx or _ffi.default_context()
+        self.lib = self.ctx.lib
+        yp, un = _float_col(y_pred), _float_col(uncertainty)
+        if yp.dtype != un.dtype:       # mixed float widths: promote both (documented deviation)
+            yp, un = yp.astype(np.float64), un.astype(np.float64)
+        self.dtype = yp.dtype
+        self.code = _ffi.BQ_F32 if self.dtype == np.float32 else _ffi.BQ_F64
+        self.n = int(yp.shape[0])
+        yt = _label_col(y_true)
+        if un.shape[0] != self.n or yt.shape[0] != self.n:
+            raise ValueError("y_true, y_pred and uncertainty must have the same length")
+        h = C.c_void_p()
+        _ffi.check(self.ctx.handle,
+                   self.lib.bq_table_create(self.ctx.handle, self.n, self.code, _ffi.ptr(yp),
+                                            _ffi.ptr(un), _ffi.ptr(yt), C.byref(h)),
+                   "bq_table_create")
+        self.h = h
+        self.n_groups = 0
+
+    def close(self):
+        if self.h:
+            self.lib.bq_table_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- threshold.py:141 + sklearn input checks
+    def validate(self):
+        flags = (C.c_int64 * 4)()
+        _ffi.check(self.ctx.handle, self.lib.bq_table_validate(self.h, flags), "bq_table_validate")
+        return tuple(int(f) for f in flags)
+
+    def tile_process(self, pred_thresh_eff: float, want_columns=True):
+        n = self.n
+        err = np.empty(n, np.float64) if want_columns else None
+        cor = np.empty(n, np.uint8) if want_columns else None
+        ybin = np.empty(n, np.uint8) if want_columns else None
+        _ffi.check(self.ctx.handle,
+                   self.lib.bq_tile_process(self.h, float(pred_thresh_eff), _ffi.ptr(err),
+                                            _ffi.ptr(cor), _ffi.ptr(ybin)), "bq_tile_process")
+        return err, cor, ybin
+
+    def tile_roc(self, score_sel, label_sel):
+        r = _roc_struct()
+        _ffi.check(self.ctx.handle, self.lib.bq_tile_roc(self.h, score_sel, label_sel, C.byref(r)),
+                   "bq_tile_roc")
+        return r
+
+    def set_groups(self, codes: np.ndarray, n_groups: int):
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        _ffi.check(self.ctx.handle, self.lib.bq_table_set_groups(self.h, _ffi.ptr(codes), int(n_groups)),
+                   "bq_table_set_groups")
+        self.n_groups = int(n_groups)
+
+    def set_filter(self, tile_uq_eff):
+        if tile_uq_eff is None:
+            rc = self.lib.bq_table_set_tile_filter(self.h, 0, 0.0)
+        else:
+            rc = self.lib.bq_table_set_tile_filter(self.h, 1, float(tile_uq_eff))
+        _ffi.check(self.ctx.handle, rc, "bq_table_set_tile_filter")
+
+    def group_reduce(self):
+        L = self.n_groups
+        gp, gu = np.empty(L, self.dtype), np.empty(L, self.dtype)
+        gt = np.empty(L, np.float64)
+        cnt, first = np.empty(L, np.int64), np.empty(L, np.int64)
+        _ffi.check(self.ctx.handle,
+                   self.lib.bq_group_reduce(self.h, _ffi.ptr(gp), _ffi.ptr(gu), _ffi.ptr(gt),
+                                            _ffi.ptr(cnt), _ffi.ptr(first)), "bq_group_reduce")
+        return gp, gu, gt, cnt, first
+
+
+def _roc(ctx, score, label, include=None):
+    """bq_roc on host arrays -> RocResult."""
+    score = _float_col(np.asarray(score))
+    label = np.ascontiguousarray(label, dtype=np.uint8)
+    inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+    r = _roc_struct()
+    code = _ffi.BQ_F32 if score.dtype == np.float32 else _ffi.BQ_F64
+    _ffi.check(ctx.handle,
+               ctx.lib.bq_roc(ctx.handle, _ffi.ptr(score), code, _ffi.ptr(label), _ffi.ptr(inc),
+                              int(score.shape[0]), C.byref(r)), "bq_roc")
+    return r
+
+
+def _youden_or_raise(r):
+    """The reference's `max(zip(tpr,fpr))` / `.index()` idiom raises ValueError for single-class
+    labels; empty input makes sklearn raise ValueError too."""
+    if r.status != 0:
+        raise ValueError("(nan, nan) is not in list" if r.status == 1
+                         else "Found array with 0 sample(s) while a minimum of 1 is required.")
+    return np.float64(r.threshold)
+
+
+def _check_columns(df):
+    missing = [c for c in ("y_true", "y_pred", "uncertainty") if c not in df.columns]
+    if missing:
+        raise ValueError("Missing columns. Expected y_true, y_pred, uncertainty. "
+                         f"Got: {', '.join(map(str, df.columns))}")
+
+
+def _open_table(df, ctx=None) -> _DeviceTable:
+    unc = df["uncertainty"].to_numpy() if "uncertainty" in df.columns else np.zeros(len(df), df["y_pred"].to_numpy().dtype)
+    return _DeviceTable(df["y_pred"].to_numpy(), unc, df["y_true"].to_numpy(), ctx=ctx)
+
+
+# ----------------------------------------------------------------------------------------
+# tile level
+# ----------------------------------------------------------------------------------------
+
+def _tile_stage(tab: _DeviceTable, df, pred_thresh, patients):
+    """threshold.py:140-177 on an open device table; mutates df; returns pred_thresh used."""
+    n_nan, n_nonfinite, _, n_badlabel = tab.validate()
+    if n_nan:                                                         # :141-142
+        raise errors.PredsContainNaNError
+    if n_nonfinite:
+        raise ValueError("Input contains infinity or a value too large for dtype.")
+    if n_badlabel:
+        raise ValueError("multiclass format is not supported")
+    if _is_detect(pred_thresh):                                       # :145-159
+        r = tab.tile_roc(_ffi.SCORE_Y_PRED, _ffi.LABEL_Y_TRUE)
+        if r.status == 0:
+            pred_thresh = np.float64(r.threshold)
+        elif r.status == 1:
+            log.debug("Unable to calculate tile prediction threshold; using 0.5")
+            pred_thresh = 0.5                                         # :153-155
+        else:
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
+        log.debug(f"Auto-detected tile prediction threshold: {pred_thresh:.4f}")
+    else:
+        if tab.n == 0:
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
+        log.debug(f"Using tile prediction threshold: {pred_thresh:.4f}")  # :161
+    if patients is not None:                                          # :163-166
+        df["patient"] = df["slide"].map(patients)
+    else:
+        log.debug("Patients not provided; assuming 1:1 slide:patient mapping")
+    err, cor, ybin = tab.tile_process(_cmp_scalar(pred_thresh, df["y_pred"].to_numpy().dtype))
+    # dtypes as pandas gives them: |int64 - float| -> float64 (narrow ints keep the float width)
+    err_dtype = np.result_type(df["y_true"].to_numpy().dtype, df["y_pred"].to_numpy().dtype)
+    df["error"] = err if err_dtype == np.float64 else err.astype(err_dtype)   # :170
+    df["correct"] = cor.view(np.bool_)                                # :171-174
+    df["incorrect"] = (cor ^ 1).astype(int)                           # :175
+    df["y_pred_bin"] = ybin.astype(int)                               # :176
+    return pred_thresh
+
+
+def process_tile_predictions(df, pred_thresh=0.5, patients=None):
+    """Tile-level processing (reference threshold.py:125-177).
+
+    Adds `error`, `correct`, `incorrect`, `y_pred_bin` (and `patient`) to `df` IN PLACE and returns
+    ``(df, pred_thresh)``; ``pred_thresh='detect'`` picks Youden's J on the tile ROC."""
+    with _open_table(df) as tab:
+        pred_thresh = _tile_stage(tab, df, pred_thresh, patients)
+    return df, pred_thresh
+
+
+# ----------------------------------------------------------------------------------------
+# group (slide / patient) level
+# ----------------------------------------------------------------------------------------
+
+def _factorize(keys: pd.Series):
+    codes, uniques = pd.factorize(keys, use_na_sentinel=True)   # first-appearance order, NaN -> -1
+    return codes.astype(np.int32, copy=False), uniques
+
+
+def _group_stage(tab: _DeviceTable, df, level, tile_uq_eff, pred_thresh, factorized=None):
+    """threshold.py:188-245 with the tile-UQ filter (threshold.py:298/412/426) applied on the
+    device.  Returns (group DataFrame, pred_thresh used)."""
+    codes, uniques = factorized if factorized is not None else _factorize(df[level])
+    tab.set_groups(codes, len(uniques))
+    tab.set_filter(tile_uq_eff)
+    gp, gu, gt, cnt, first = tab.group_reduce()
+    alive = np.flatnonzero(cnt > 0)
+    order = alive[np.argsort(first[alive], kind="stable")]           # first appearance after filter
+    levels = [uniques[i] for i in order]                              # :190
+    yp, u = gp[order], gu[order]
+    yt = gt[order].astype(np.uint8)                                   # :197-200 truncation
+    if not len(yt):                                                   # :205-206
+        raise errors.ROCFailedError("Unable to generate ROC; preds are empty.")
+    if _is_detect(pred_thresh):                                       # :217-223
+        r = _roc(tab.ctx, yp, yt)
+        if r.status != 0:
+            raise errors.ROCFailedError(f"Unable to generate {level}-level ROC")
+        pred_thresh = np.float64(r.threshold)
+        log.debug(f"Using detected prediction threshold: {pred_thresh:.4f}")
+    else:
+        log.debug(f"Using {level} prediction threshold: {pred_thresh:.4f}")   # :225
+    cols = _group_columns(tab.ctx, yp, u, yt, pred_thresh, pred_thresh, _ffi.KEEP_ALL, 0.0)
+    l_df = pd.DataFrame({                                             # :235-244
+        level: pd.Series(levels),
+        "error": pd.Series(cols["error"]),
+        "uncertainty": pd.Series(u),
+        "correct": cols["correct"].view(np.bool_),
+        "incorrect": pd.Series(cols["incorrect"]).astype(int),
+        "y_true": pd.Series(yt),
+        "y_pred": pd.Series(yp),
+        "y_pred_bin": pd.Series(cols["y_pred_bin"].view(np.bool_)).astype(int),
+    })
+    return l_df, pred_thresh
+
+
+def _group_columns(ctx, yp, u, yt, pred_thresh, strict_thresh, keep_mode, slide_uq_eff):
+    L = int(yp.shape[0])
+    dt = yp.dtype
+    code = _ffi.BQ_F32 if dt == np.float32 else _ffi.BQ_F64
+    out = {"error": np.empty(L, dt), "correct": np.empty(L, np.uint8), "incorrect": np.empty(L, np.uint8),
+           "y_pred_bin": np.empty(L, np.uint8), "include": np.empty(L, np.uint8)}
+    conf = (C.c_int64 * 4)()
+    yp, u, yt = np.ascontiguousarray(yp), np.ascontiguousarray(u), np.ascontiguousarray(yt)
+    _ffi.check(ctx.handle,
+               ctx.lib.bq_group_apply(ctx.handle, L, code, _ffi.ptr(yp), _ffi.ptr(u), _ffi.ptr(yt),
+                                      _cmp_scalar(pred_thresh, dt), _cmp_scalar(strict_thresh, dt),
+                                      int(keep_mode), float(slide_uq_eff),
+                                      _ffi.ptr(out["error"]), _ffi.ptr(out["correct"]),
+                                      _ffi.ptr(out["incorrect"]), _ffi.ptr(out["y_pred_bin"]),
+                                      _ffi.ptr(out["include"]), conf), "bq_group_apply")
+    out["confusion"] = tuple(np.int64(c) for c in conf)
+    return out
+
+
+def process_group_predictions(df, pred_thresh, level):
+    """Group-level (slide / patient) predictions and uncertainty from tile-level rows
+    (reference threshold.py:180-245): per-group means in first-appearance order, `y_true`
+    truncated to uint8, `correct / incorrect / y_pred_bin` with ``>= pred_thresh``.
+    ``pred_thresh='detect'`` picks Youden's J on the group ROC (ROCFailedError if impossible)."""
+    _check_columns(df)
+    if len(df) == 0:
+        df[level]                                                     # KeyError parity
+        raise errors.ROCFailedError("Unable to generate ROC; preds are empty.")
+    with _open_table(df) as tab:
+        return _group_stage(tab, df, level, None, pred_thresh)
+
+
+def _auc_included(ctx, s_yp, s_yt, include=None):
+    """utils.py:487-504: ROC AUC of the surviving groups, NaN when undefined."""
+    r = _roc(ctx, s_yp, s_yt, include)
+    if r.status == 2:
+        log.warning("Unable to calculate ROC")
+        return np.nan
+    return float(r.auc)
+
+
+def apply(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
+          keep="high_confidence", title=None, patients=None, level="slide"):
+    """Apply pre-calculated tile- and group-level uncertainty thresholds
+    (reference threshold.py:248-361).
+
+    Args:
+        df (pandas.DataFrame): columns 'y_true', 'y_pred', 'uncertainty', 'slide'. Mutated in place
+            exactly like the reference (adds error / correct / incorrect / y_pred_bin / patient).
+        tile_uq (float): tile-level uncertainty threshold (falsy: no tile filter).
+        slide_uq (float): group-level uncertainty threshold (falsy: no group filter).
+        tile_pred, slide_pred (float): prediction thresholds. Default 0.5.
+        keep (str): 'high_confidence' (uncertainty < slide_uq) or 'low_confidence' (>=).
+        patients (dict): slide -> patient; required for level='patient'.
+        level (str): 'slide' or 'patient'.
+
+    Returns:
+        dict with auc, percent_incl, acc, sensitivity, specificity; DataFrame of the kept groups
+        (original integer index labels).  ({...None}, None) if no group-level ROC is possible."""
+    assert keep in ("high_confidence", "low_confidence")             # :281
+    assert not (level == "patient" and patients is None)             # :282
+    log.debug(f"Applying tile UQ threshold of {tile_uq:.5f}")         # :284 (TypeError on None)
+    if plot:
+        log.warning("plot=True ignored: plotting is outside the scope of biscuit_b200")
+    if patients:                                                      # :285-286
+        df["patient"] = df["slide"].map(patients)
+    df[level]                                                         # :287 KeyError parity
+    _check_columns(df)
+    with _open_table(df) as tab:
+        _tile_stage(tab, df, tile_pred, patients)                     # :290-294
+        fact = _factorize(df[level])
+        n_before = len(fact[1]) + int((fact[0] < 0).any())            # :295 (NaN counts as a key)
+        unc_dtype = tab.dtype
+        tile_uq_eff = _cmp_scalar(tile_uq, unc_dtype) if tile_uq else None   # :297-298
+        try:
+            s_df, _ = _group_stage(tab, df, level, tile_uq_eff, slide_pred, factorized=fact)  # :305
+        except errors.ROCFailedError:
+            log.error("Unable to process slide predictions")
+            return {k: None for k in _RESULT_KEYS}, None              # :310-317
+        ctx = tab.ctx
+    yp, u, yt = s_df["y_pred"].to_numpy(), s_df["uncertainty"].to_numpy(), s_df["y_true"].to_numpy()
+    if slide_uq:                                                      # :323-330
+        log.debug(f"Using {level} uncertainty threshold of {slide_uq:.5f}")
+        mode = _ffi.KEEP_HIGH if keep == "high_confidence" else _ffi.KEEP_LOW
+        uq_eff = _cmp_scalar(slide_uq, u.dtype)
+    else:
+        mode, uq_eff = _ffi.KEEP_ALL, 0.0
+    cols = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, mode, uq_eff)
+    include = cols["include"].view(np.bool_)
+    if slide_uq:
+        s_df = s_df.loc[include]
+    auc = _auc_included(ctx, yp, yt, cols["include"])                 # :333
+    percent_incl = len(s_df) / n_before                               # :334-335
+    tp, fp, tn, fn = cols["confusion"]                                # :339-345
+    with np.errstate(invalid="ignore", divide="ignore"):
+        results = {"auc": auc, "percent_incl": percent_incl,
+                   "acc": (tp + tn) / (tp + tn + fp + fn),            # :346
+                   "sensitivity": tp / (tp + fn),                     # :347
+                   "specificity": tn / (tn + fp)}                     # :348
+    return results, s_df
+
+
+def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pred="detect",
+           plot=False, patients=None):
+    """Detect optimal tile- and slide-level uncertainty thresholds (reference threshold.py:364-475).
+
+    Each of tile_uq / slide_uq / tile_pred / slide_pred is 'detect' (Youden's J on the matching
+    ROC) or a float to use as given.  Returns (dict of the four thresholds, slide-level AUROC), or
+    (all-None dict, None) when predictions contain NaN or no slide-level ROC is possible."""
+    none4 = {k: None for k in _THRESH_KEYS}
+    if plot:
+        log.warning("plot=True ignored: plotting is outside the scope of biscuit_b200")
+    _check_columns(df)
+    with _open_table(df) as tab:
+        try:
+            found_tile_pred = _tile_stage(tab, df, tile_pred, patients)   # :398-402
+        except errors.PredsContainNaNError:
+            log.error("Tile-level predictions contain NaNs; unable to process.")
+            return none4, None                                        # :403-405
+        if _is_detect(tile_pred):                                     # :407-408
+            tile_pred = found_tile_pred
+        if isinstance(tile_uq, _FLOAT_TYPES):                         # :411-412
+            tile_uq_eff = _cmp_scalar(tile_uq, tab.dtype)
+        elif not _is_detect(tile_uq):                                 # :413-415
+            log.debug("Not performing tile-level uncertainty thresholding.")
+            tile_uq, tile_uq_eff = None, None
+        else:                                                         # :416-426
+            r = tab.tile_roc(_ffi.SCORE_UNCERTAINTY, _ffi.LABEL_INCORRECT)
+            tile_uq = _youden_or_raise(r)
+            log.debug(f"Tile-level optimal UQ threshold: {tile_uq:.4f}")
+            tile_uq_eff = float(tile_uq)
+        try:
+            s_df, slide_pred = _group_stage(tab, df, "slide", tile_uq_eff, slide_pred)  # :433-438
+        except errors.ROCFailedError:
+            log.error("Unable to process slide predictions")
+            return none4, None                                        # :439-441
+        ctx = tab.ctx
+    yp, u, yt = s_df["y_pred"].to_numpy(), s_df["uncertainty"].to_numpy(), s_df["y_true"].to_numpy()
+    include = None
+    if _is_detect(slide_uq):                                          # :444-460
+        inc = s_df["incorrect"].to_numpy()
+        if not inc.sum():
+            log.debug("Unable to calculate slide UQ threshold; no incorrect predictions made")
+            slide_uq = None
+        else:
+            slide_uq = _youden_or_raise(_roc(ctx, u, inc))
+            log.debug(f"Slide-level optimal UQ threshold: {slide_uq:.4f}")
+            include = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, _ffi.KEEP_HIGH,
+                                     float(slide_uq))["include"]
+    else:
+        log.debug("Not performing slide-level uncertainty thresholding.")
+        slide_uq = 0.5                                                # :461-463
+    auc = _auc_included(ctx, yp, yt, include)                         # :468
+    return {"tile_uq": tile_uq, "slide_uq": slide_uq,
+            "tile_pred": tile_pred, "slide_pred": slide_pred}, auc
+
+
+def from_cv(dfs, **kwargs):
+    """Optimal tile- and slide-level thresholds from a set of (nested) cross-validation folds
+    (reference threshold.py:478-557): `detect` per fold, folds without a tile_uq / slide_uq are
+    skipped, then tile_uq = min, slide_uq = max, tile_pred / slide_pred = mean over folds.
+
+    Args:
+        dfs (list(DataFrame)): tile predictions with 'y_true', 'y_pred', 'uncertainty', 'slide',
+            'patient'.
+        **kwargs: forwarded to :func:`detect` (tile_uq, slide_uq, tile_pred, slide_pred, patients).
+
+    Raises ValueError for missing columns and ThresholdError when no fold yields a threshold."""
+    required = ("y_true", "y_pred", "uncertainty", "slide", "patient")
+    skip_tile = "tile_uq_thresh" in kwargs and kwargs["tile_uq_thresh"] is None     # :513-516
+    skip_slide = "slide_uq_thresh" in kwargs and kwargs["slide_uq_thresh"] is None
+    k_tile, k_slide, k_tile_pred, k_slide_pred = [], [], [], []
+    for idx, df in enumerate(dfs):
+        log.debug(f"Detecting thresholds from fold {idx}")
+        if not all(col in df.columns for col in required):            # :520-524
+            raise ValueError(f"DataFrame missing columns, expected {required}, got: "
+                             f"{', '.join(df.columns.tolist())}")
+        thresholds, _ = detect(df, **kwargs)                          # :525
+        if thresholds["tile_uq"] is None or thresholds["slide_uq"] is None:   # :526-528
+            log.debug(f"Skipping CV #{idx}, unable to detect threshold")
+            continue
+        k_tile_pred.append(thresholds["tile_pred"])
+        k_slide_pred.append(thresholds["slide_pred"])
+        if not skip_tile:
+            k_tile.append(thresholds["tile_uq"])
+        if not skip_slide:
+            k_slide.append(thresholds["slide_uq"])
+    if not skip_tile and not len(k_tile):                             # :539-542
+        raise errors.ThresholdError("Unable to detect tile UQ threshold.")
+    if not skip_slide and not len(k_slide):
+        raise errors.ThresholdError("Unable to detect slide UQ threshold.")
+    return {                                                          # :544-557
+        "tile_uq": np.min(k_tile) if not skip_tile else k_tile,
+        "slide_uq": np.max(k_slide) if not skip_slide else k_slide,
+        "tile_pred": np.mean(k_tile_pred),
+        "slide_pred": np.mean(k_slide_pred),
+    }
