@@ -1,0 +1,393 @@
+// Dense bf16 GEMM with fused epilogue on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+//
+//   D[M,N] = epilogue( A[M,K] * B[N,K]^T ),   A, B bf16 K-major, fp32 accumulation in TMEM
+//   epilogue: v = acc * scale[n] + shift[n] (+ residual[m,n]) -> optional ReLU -> bf16
+//
+// It carries every GEMM-shaped op of the Xception-UQ hot path (K2, K3 pointwise, K4, and the
+// dense layers of the MC-dropout head):
+//   * pointwise 1x1 convolutions: A = NHWC activations viewed as [B*H*W, Cin], B = weights [Cout, Cin];
+//     BatchNorm is the per-channel scale/shift, ReLU and the residual add ride in the epilogue;
+//   * block1_conv2 (3x3 valid, 32->64) as an implicit GEMM: K-block kb is filter tap (kb/3, kb%3) and the A
+//     tile of that tap is the SAME 2-D activation matrix shifted by (ky*W + kx) rows, so one TMA descriptor
+//     serves all nine taps; rows whose (y, x) fall outside the valid output window are dropped in the epilogue;
+//   * dense layers: scale = 1 (or 1/(1-p) after a dropout site), shift = bias.
+//
+// Structure (one CTA per SM, persistent over output tiles, warp specialised):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d into a STAGES-deep smem ring (128B / 64B swizzle)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x 256 cols)
+//   warps 2-5: epilogue      -- tcgen05.ld 32x32b.x32 -> registers -> scale/shift/residual/ReLU -> bf16 -> 16 B stores
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bq {
+
+struct GemmParams {
+  int M = 0;               // rows of D (conv mode: virtual rows over the INPUT grid)
+  int N = 0;               // output channels
+  int K = 0;               // reduction length (conv mode: 9 * Cin)
+  int bn_box = 256;        // rows of the B TMA box == N-tile width (multiple of 16, <= 256)
+  const float* scale = nullptr;   // [round_up(N,256)] per-channel scale, nullptr -> alpha
+  const float* shift = nullptr;   // [round_up(N,256)] per-channel shift, nullptr -> 0
+  float alpha = 1.0f;
+  const __nv_bfloat16* residual = nullptr;   // [M, ldr] added before the ReLU
+  int ldr = 0;
+  __nv_bfloat16* out = nullptr;              // [M, ldc]
+  int ldc = 0;
+  int relu = 0;
+  // implicit 3x3 valid convolution (conv_mode = 1): virtual row m = img*in_hw + y*in_w + x
+  int conv_mode = 0;
+  int in_w = 0, in_hw = 0, out_w = 0, out_h = 0, out_hw = 0;
+  // debug path only (SIMT kernel reads the operands directly)
+  const __nv_bfloat16* a_ptr = nullptr;
+  int lda = 0;
+  long long a_rows = 0;
+  const __nv_bfloat16* b_ptr = nullptr;
+  int ldb = 0;
+};
+
+namespace sm100 {
+
+constexpr int kBM = 128;        // UMMA M (cta_group::1)
+constexpr int kBNMax = 256;     // UMMA N max
+constexpr int kThreads = 192;   // 6 warps
+constexpr int kAccStages = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch failure), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("bq gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of SWIZZLE bytes, 8-row groups.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1
+//   | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2ull : (SWIZZLE_BYTES == 64 ? 4ull : 6ull);
+  constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_K>
+struct SmemPlan {
+  static constexpr int kStages = BLOCK_K == 64 ? 4 : 6;
+  static constexpr int kABytes = kBM * BLOCK_K * 2;
+  static constexpr int kBBytes = kBNMax * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + tmem slot, + slack for 1024 B alignment
+};
+
+template <int BLOCK_K>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Plan = SmemPlan<BLOCK_K>;
+  constexpr int STAGES = Plan::kStages;
+  constexpr int SWZ = BLOCK_K * 2;     // bytes per smem row == swizzle span
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Plan::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kAccStages + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages);
+  volatile uint32_t* tmem_slot_ptr =
+      (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + p.bn_box - 1) / p.bn_box;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = p.conv_mode ? 9 : (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t stage_tx = Plan::kABytes + (uint32_t)p.bn_box * BLOCK_K * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < kAccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), stage_tx);
+          const uint32_t a_dst = smem_base + s * Plan::kStageBytes, b_dst = a_dst + Plan::kABytes;
+          if (p.conv_mode) {
+            tma_load_2d(a_dst, &tmap_a, full_bar(s), 0, m0 + (kb / 3) * p.in_w + (kb % 3));
+          } else {
+            tma_load_2d(a_dst, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
+          }
+          tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * p.bn_box;
+        int n_cols = p.N - n0;
+        if (n_cols > p.bn_box) n_cols = p.bn_box;
+        n_cols = (n_cols + 15) & ~15;
+        const uint32_t idesc = make_idesc(kBM, n_cols);
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + s * Plan::kStageBytes, b_src = a_src + Plan::kABytes;
+          int ksteps = BLOCK_K / 16;
+          if (!p.conv_mode && kb == num_kb - 1) {
+            const int tail = p.K - kb * BLOCK_K;     // TMA zero-fills columns >= K
+            ksteps = (tail + 15) / 16;
+          }
+          const uint64_t da = make_smem_desc<SWZ>(a_src), db = make_smem_desc<SWZ>(b_src);
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));                       // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++as == kAccStages) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
+    const int quad = warp & 3;
+    int as = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
+      int n_cols = p.N - n0;
+      if (n_cols > p.bn_box) n_cols = p.bn_box;
+      const int m = m0 + quad * 32 + lane;
+      // output row (conv mode drops rows outside the valid window and compacts the rest)
+      long long orow = m;
+      bool row_ok = m < p.M;
+      if (p.conv_mode && row_ok) {
+        const int img = m / p.in_hw, rem = m - img * p.in_hw;
+        const int y = rem / p.in_w, x = rem - y * p.in_w;
+        row_ok = (y < p.out_h) && (x < p.out_w);
+        orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
+      }
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
+      for (int c = 0; c < n_cols; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int n = n0 + c;
+          __nv_bfloat16* optr = p.out + orow * p.ldc + n;
+          const __nv_bfloat16* rptr = p.residual ? p.residual + orow * p.ldr + n : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n + g * 8 < p.N) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              // separately rounded multiply and add (no FMA contraction): same rounding sequence as the
+              // oracle's `acc * scale + shift`
+              if (p.scale) {
+                const float4 s0 = __ldg((const float4*)(p.scale + n + g * 8));
+                const float4 s1 = __ldg((const float4*)(p.scale + n + g * 8 + 4));
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], sc[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], p.alpha);
+              }
+              if (p.shift) {
+                const float4 h0 = __ldg((const float4*)(p.shift + n + g * 8));
+                const float4 h1 = __ldg((const float4*)(p.shift + n + g * 8 + 4));
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], sh[j]);
+              }
+              if (rptr) {
+                const uint4 r = *(const uint4*)(rptr + g * 8);
+                const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 rf = __bfloat1622float2(rb[j]);
+                  f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4 o;
+              __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *(uint4*)(optr + g * 8) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == kAccStages) { as = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace sm100
+
+// ---- debug-only SIMT GEMM with the same parameter block (BQ_GEMM=simt); slow, obviously correct ----
+__global__ void gemm_simt_kernel(const GemmParams p) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 32 + ty, n = blockIdx.x * 32 + tx;
+  const int taps = p.conv_mode ? 9 : 1;
+  const int kc = p.conv_mode ? p.K / 9 : p.K;
+  float acc = 0.f;
+  for (int t = 0; t < taps; ++t) {
+    const long long roff = p.conv_mode ? (long long)(t / 3) * p.in_w + (t % 3) : 0;
+    for (int k0 = 0; k0 < kc; k0 += 32) {
+      const long long ar = (long long)(blockIdx.y * 32 + ty) + roff;
+      const int ak = k0 + tx;
+      As[ty][tx] = (ar < p.a_rows && ak < kc) ? __bfloat162float(p.a_ptr[ar * p.lda + ak]) : 0.f;
+      const int bn = blockIdx.x * 32 + ty;
+      Bs[ty][tx] = (bn < p.N && ak < kc) ? __bfloat162float(p.b_ptr[(long long)bn * p.ldb + t * kc + ak]) : 0.f;
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
+      __syncthreads();
+    }
+  }
+  if (m >= p.M || n >= p.N) return;
+  long long orow = m;
+  if (p.conv_mode) {
+    const int img = m / p.in_hw, rem = m - img * p.in_hw;
+    const int y = rem / p.in_w, x = rem - y * p.in_w;
+    if (y >= p.out_h || x >= p.out_w) return;
+    orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
+  }
+  float v = __fmul_rn(acc, p.scale ? p.scale[n] : p.alpha);
+  if (p.shift) v = __fadd_rn(v, p.shift[n]);
+  if (p.residual) v = __fadd_rn(v, __bfloat162float(p.residual[orow * p.ldr + n]));
+  if (p.relu) v = fmaxf(v, 0.f);
+  p.out[orow * p.ldc + n] = __float2bfloat16_rn(v);
+}
+
+}  // namespace bq

@@ -1,0 +1,408 @@
+// Bandwidth-bound layers of the Xception-UQ path (NHWC, bf16 storage, fp32 math), coalesced 16-byte accesses:
+//   tile_stats  -- per-tile mean / 1/std over the uint8 tile (tf.image.per_image_standardization, results.py:255)
+//   conv1       -- uint8 decode + standardise fused into block1_conv1 (3x3 s2 valid, 3->32) + BN + ReLU
+//   depthwise   -- 3x3 'same' depthwise conv of every SeparableConv2D (optional ReLU on the input)
+//   pool_add    -- MaxPool 3x3 s2 'same' (TF padding, -inf) + residual add
+//   subsample   -- stride-2 pixel gather feeding the 1x1 s2 residual convolutions
+//   gap         -- global average pooling -> 2048 features
+//   head        -- Philox4x32-10 dropout masks, masked operand expansion, logits + softmax + mean/std over T
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bq {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* b = (const __nv_bfloat162*)&v;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(b[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
+  uint4 o;
+  __nv_bfloat162* b = (__nv_bfloat162*)&o;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-tile statistics: exact integer sums, fp64 finish.  One block per tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, float* __restrict__ mean,
+                  float* __restrict__ inv_std) {
+  const uint8_t* src = tiles + (int64_t)blockIdx.x * bytes_per_tile;
+  unsigned long long s = 0, s2 = 0;
+  // head up to 16-byte alignment, vector body, tail
+  const uintptr_t addr = (uintptr_t)src;
+  int64_t head = (16 - (addr & 15)) & 15;
+  if (head > bytes_per_tile) head = bytes_per_tile;
+  const int64_t nvec = (bytes_per_tile - head) / 16;
+  const uint4* vsrc = (const uint4*)(src + head);
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = __ldg(vsrc + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    unsigned ls = 0, ls2 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const unsigned x = (w[k] >> (8 * b)) & 0xFFu;
+        ls += x;
+        ls2 += x * x;
+      }
+    }
+    s += ls;
+    s2 += ls2;
+  }
+  const int64_t tail0 = head + nvec * 16;
+  for (int64_t i = threadIdx.x; i < head + (bytes_per_tile - tail0); i += blockDim.x) {
+    const int64_t j = i < head ? i : tail0 + (i - head);
+    const unsigned x = src[j];
+    s += x;
+    s2 += x * x;
+  }
+  __shared__ unsigned long long sh[2][16];
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long ts = 0, ts2 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += sh[0][w]; ts2 += sh[1][w]; }
+    const double n = (double)bytes_per_tile;
+    const double m = (double)ts / n;
+    double var = (double)ts2 / n - m * m;
+    if (var < 0.0) var = 0.0;
+    double sd = sqrt(var);
+    const double floor_sd = 1.0 / sqrt(n);
+    if (sd < floor_sd) sd = floor_sd;
+    mean[blockIdx.x] = (float)m;
+    inv_std[blockIdx.x] = (float)(1.0 / sd);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block1_conv1: uint8 NHWC [n,299,299,3] -> bf16 NHWC [n,149,149,32]; 3x3 stride 2 valid, BN, ReLU.
+// A block computes a 16x16 output patch: the 33x33x3 input patch is standardised into smem as fp32 once,
+// each thread owns one output pixel x 32 channels (fp32 weights broadcast from smem).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kC1Tile = 16;
+constexpr int kC1In = 2 * kC1Tile + 1;
+__global__ void __launch_bounds__(256)
+conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, const float* __restrict__ inv_std,
+             const float* __restrict__ w /*[27][32]*/, const float* __restrict__ scale, const float* __restrict__ shift,
+             bf16* __restrict__ out, int in_px, int out_px) {
+  __shared__ float patch[kC1In * kC1In * 3];
+  __shared__ float ws[27 * 32];
+  __shared__ float sc[32], sh[32];
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
+  const float mu = mean[img], is = inv_std[img];
+  const uint8_t* src = tiles + (int64_t)img * in_px * in_px * 3;
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 32) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+  const int iy0 = oy0 * 2, ix0 = ox0 * 2;
+  for (int i = threadIdx.x; i < kC1In * kC1In * 3; i += blockDim.x) {
+    const int r = i / (kC1In * 3), rem = i - r * (kC1In * 3);
+    const int y = iy0 + r, xc = ix0 * 3 + rem;
+    float v = 0.f;
+    if (y < in_px && xc < in_px * 3) v = __fmul_rn(__fadd_rn((float)src[(int64_t)y * in_px * 3 + xc], -mu), is);
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kC1Tile, tx = threadIdx.x % kC1Tile;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy >= out_px || ox >= out_px) return;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float x = patch[((2 * ty + ky) * kC1In + (2 * tx + kx)) * 3 + ci];
+        const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+      }
+    }
+  }
+  bf16* o = out + (((int64_t)img * out_px + oy) * out_px + ox) * 32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      f[j] = fmaxf(__fadd_rn(__fmul_rn(acc[c], sc[c]), sh[c]), 0.f);
+    }
+    *(uint4*)(o + g * 8) = float_to_bf16x8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// depthwise 3x3, stride 1, 'same' (zero pad 1).  One thread = one pixel x 8 channels (16 B).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depthwise3x3_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][C]*/, bf16* __restrict__ out,
+                    int n_img, int H, int W, int C, int relu_in) {
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)n_img * H * W * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    int64_t pix = idx / cv;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const int img = (int)(pix / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bf16* base = in + ((int64_t)img * H * W) * C + c8 * 8;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 v = __ldg((const uint4*)(base + ((int64_t)yy * W + xx) * C));
+        float f[8];
+        bf16x8_to_float(v, f);
+        const float4 w0 = __ldg((const float4*)(w + (ky * 3 + kx) * C + c8 * 8));
+        const float4 w1 = __ldg((const float4*)(w + (ky * 3 + kx) * C + c8 * 8 + 4));
+        const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xv = relu_in ? fmaxf(f[j], 0.f) : f[j];
+          acc[j] = fmaf(xv, wf[j], acc[j]);
+        }
+      }
+    }
+    *(uint4*)(out + (((int64_t)img * H + y) * W + x) * C + c8 * 8) = float_to_bf16x8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MaxPool 3x3 stride 2 'same' (TF: pad_total = max((ceil(H/2)-1)*2 + 3 - H, 0), before = total/2) + residual
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_add_kernel(const bf16* __restrict__ in, const bf16* __restrict__ res, bf16* __restrict__ out, int n_img,
+                   int H, int W, int Ho, int Wo, int C, int pad_top, int pad_left) {
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)n_img * Ho * Wo * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    int64_t pix = idx / cv;
+    const int xo = (int)(pix % Wo);
+    pix /= Wo;
+    const int yo = (int)(pix % Ho);
+    const int img = (int)(pix / Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    const bf16* base = in + ((int64_t)img * H * W) * C + c8 * 8;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = yo * 2 + ky - pad_top;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = xo * 2 + kx - pad_left;
+        if (xx < 0 || xx >= W) continue;
+        float f[8];
+        bf16x8_to_float(__ldg((const uint4*)(base + ((int64_t)yy * W + xx) * C)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    const int64_t o = (((int64_t)img * Ho + yo) * Wo + xo) * C + c8 * 8;
+    float r[8];
+    bf16x8_to_float(__ldg((const uint4*)(res + o)), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = __fadd_rn(m[j], r[j]);
+    *(uint4*)(out + o) = float_to_bf16x8(m);
+  }
+}
+
+// stride-2 pixel gather: out[n,yo,xo,:] = in[n,2yo,2xo,:]   (1x1 stride-2 'valid' conv samples 0,2,4,...)
+__global__ void __launch_bounds__(256)
+subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n_img, int H, int W, int Ho, int Wo, int C) {
+  const int cv = C >> 3;
+  const int64_t total = (int64_t)n_img * Ho * Wo * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    int64_t pix = idx / cv;
+    const int xo = (int)(pix % Wo);
+    pix /= Wo;
+    const int yo = (int)(pix % Ho);
+    const int img = (int)(pix / Ho);
+    const uint4 v = __ldg((const uint4*)(in + (((int64_t)img * H + 2 * yo) * W + 2 * xo) * C + c8 * 8));
+    *(uint4*)(out + (((int64_t)img * Ho + yo) * Wo + xo) * C + c8 * 8) = v;
+  }
+}
+
+// global average pool: [n, HW, C] bf16 -> fp32 [n, C] (+ bf16 copy as the next GEMM's A operand)
+__global__ void __launch_bounds__(256)
+gap_kernel(const bf16* __restrict__ in, float* __restrict__ feat, bf16* __restrict__ feat_bf16, int n_img, int HW, int C) {
+  const int64_t total = (int64_t)n_img * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int img = (int)(idx / C);
+    const bf16* p = in + (int64_t)img * HW * C + c;
+    float s = 0.f;
+    for (int i = 0; i < HW; ++i) s += __bfloat162float(p[(int64_t)i * C]);
+    const float m = s / (float)HW;
+    feat[idx] = m;
+    feat_bf16[idx] = __float2bfloat16_rn(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MC-dropout head pieces
+// ---------------------------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+// Philox4x32-10 (Salmon et al. 2011); same stream as oracle/xception_uq.py:philox4x32_10
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return {c0, c1, c2, c3};
+}
+
+// keep-bits of 4 consecutive hidden units e..e+3 of (tile, sample t, site): bit j set = keep unit e+j.
+// counter = (e/4, t*4 + site, tile_lo, tile_hi), key = seed; keep iff draw >= floor(rate * 2^32).
+__device__ __forceinline__ uint32_t keep4(uint64_t seed, uint64_t tile, int t, int site, int e4, uint32_t thresh) {
+  const Philox4 r = philox4x32_10((uint32_t)e4, (uint32_t)(t * 4 + site), (uint32_t)tile, (uint32_t)(tile >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (r.x >= thresh ? 1u : 0u) | (r.y >= thresh ? 2u : 0u) | (r.z >= thresh ? 4u : 0u) | (r.w >= thresh ? 8u : 0u);
+}
+
+// A2[(i*T + t), k] = keep(i, t, site, k) ? h[i, k] : 0      (one thread = 4 consecutive k)
+// masks (nullable): injected uint8 keep-masks [n, T, n_sites, width]; site_slot indexes dim 2.
+__global__ void __launch_bounds__(256)
+mc_expand_kernel(const bf16* __restrict__ h, bf16* __restrict__ a2, int n, int T, int width, uint64_t seed,
+                 uint64_t tile_base, int site, uint32_t thresh, const uint8_t* __restrict__ masks, int n_sites,
+                 int site_slot) {
+  const int w4 = width >> 2;
+  const int64_t total = (int64_t)n * T * w4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e4 = (int)(idx % w4);
+    const int64_t row = idx / w4;
+    const int t = (int)(row % T);
+    const int i = (int)(row / T);
+    uint32_t kb;
+    if (masks) {
+      const uint8_t* mp = masks + (((int64_t)i * T + t) * n_sites + site_slot) * width + e4 * 4;
+      kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
+    } else {
+      kb = keep4(seed, tile_base + (uint64_t)i, t, site, e4, thresh);
+    }
+    const uint2 v = *(const uint2*)(h + (int64_t)i * width + e4 * 4);
+    uint2 o;
+    o.x = ((kb & 1u) ? (v.x & 0xFFFFu) : 0u) | ((kb & 2u) ? (v.x & 0xFFFF0000u) : 0u);
+    o.y = ((kb & 4u) ? (v.y & 0xFFFFu) : 0u) | ((kb & 8u) ? (v.y & 0xFFFF0000u) : 0u);
+    *(uint2*)(a2 + row * width + e4 * 4) = o;
+  }
+}
+
+// Final stage, one block per tile: for every sample t, logits = ((keep .* h2[i,t,:]) @ W3) * alpha + b3,
+// softmax (2 classes... n_classes <= 8), then warp-shuffle reductions give the mean and the population std
+// over the T samples (two-pass: mean first, then sum of squared deviations).
+constexpr int kMaxClasses = 8;
+__global__ void __launch_bounds__(256)
+head_final_kernel(const bf16* __restrict__ h2 /*[n*T, width]*/, const float* __restrict__ w3 /*[width][C]*/,
+                  const float* __restrict__ b3, int T, int width, int n_classes, float alpha, int dropout_on,
+                  uint64_t seed, uint64_t tile_base, int site, uint32_t thresh, const uint8_t* __restrict__ masks,
+                  int n_sites, int site_slot, float* __restrict__ mean_out, float* __restrict__ std_out) {
+  extern __shared__ float probs[];   // [T][n_classes]
+  const int i = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nwarps) {
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) acc[c] = 0.f;
+    const bf16* row = h2 + ((int64_t)i * T + t) * width;
+    for (int e4 = lane; e4 < (width >> 2); e4 += 32) {
+      uint32_t kb = 0xFu;
+      if (dropout_on) {
+        if (masks) {
+          const uint8_t* mp = masks + (((int64_t)i * T + t) * n_sites + site_slot) * width + e4 * 4;
+          kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
+        } else {
+          kb = keep4(seed, tile_base + (uint64_t)i, t, site, e4, thresh);
+        }
+      }
+      const uint2 v = *(const uint2*)(row + e4 * 4);
+      const __nv_bfloat162* b = (const __nv_bfloat162*)&v;
+      const float2 f01 = __bfloat1622float2(b[0]), f23 = __bfloat1622float2(b[1]);
+      const float x[4] = {(kb & 1u) ? f01.x : 0.f, (kb & 2u) ? f01.y : 0.f, (kb & 4u) ? f23.x : 0.f,
+                          (kb & 8u) ? f23.y : 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* wr = w3 + (int64_t)(e4 * 4 + j) * n_classes;
+        for (int c = 0; c < n_classes; ++c) acc[c] = fmaf(x[j], __ldg(wr + c), acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane == 0) {
+      float z[kMaxClasses], mx = -INFINITY;
+      for (int c = 0; c < n_classes; ++c) {
+        z[c] = __fadd_rn(__fmul_rn(acc[c], alpha), b3[c]);
+        mx = fmaxf(mx, z[c]);
+      }
+      float den = 0.f;
+      for (int c = 0; c < n_classes; ++c) { z[c] = expf(z[c] - mx); den += z[c]; }
+      for (int c = 0; c < n_classes; ++c) probs[t * n_classes + c] = z[c] / den;
+    }
+  }
+  __syncthreads();
+  // warp c handles class c: mean then population std over T with warp-shuffle reductions
+  for (int c = warp; c < n_classes; c += nwarps) {
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) s += probs[t * n_classes + c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float m = s / (float)T;
+    float d2 = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float d = probs[t * n_classes + c] - m;
+      d2 = fmaf(d, d, d2);
+    }
+    for (int o = 16; o; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if (lane == 0) {
+      mean_out[(int64_t)i * n_classes + c] = m;
+      std_out[(int64_t)i * n_classes + c] = sqrtf(d2 / (float)T);
+    }
+  }
+}
+
+}  // namespace bq

@@ -1,11 +1,770 @@
-// placeholder until the Xception-UQ path lands (next commit)
+// Xception-UQ Monte-Carlo-dropout inference: weight packing, static execution plan, C ABI.
+//
+// Replaces slideflow.model.tensorflow.UncertaintyInterface.__call__ (call site: reference results.py:234,257;
+// architecture contract: reference biscuit/hp.py:3-24).  One backbone pass per tile, T dropout-head samples on
+// the pooled features (the reference schedule repeats the whole network T times; the backbone is deterministic in
+// inference mode, so the results are identical).  Layer list / padding rules: SURVEY.md Appendix B, restated in
+// oracle/xception_uq.py which is the parity checker for this file.
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <memory>
+
 #include "common.cuh"
-extern "C" {
-int bq_model_create(bq_ctx* ctx, const bq_model_config*, bq_model** out) { if (out) *out = nullptr; return bq_fail(ctx, BQ_ERR_STATE, "model path not built yet"); }
-void bq_model_destroy(bq_model*) {}
-int bq_model_load_weights(bq_model*, const bq_named_tensor*, int32_t) { return BQ_ERR_STATE; }
-int bq_predict_uq(bq_model*, const uint8_t*, int64_t, int32_t, uint64_t, uint64_t, const uint8_t*, float*, float*, float*) { return BQ_ERR_STATE; }
-int bq_model_debug_stage(bq_model*, const uint8_t*, int64_t, const char*, float*, int64_t, int64_t*) { return BQ_ERR_STATE; }
-int bq_model_set_profiling(bq_model*, int) { return BQ_ERR_STATE; }
-int bq_model_last_stage_ms(bq_model*, float*) { return BQ_ERR_STATE; }
+#include "gemm_sm100.cuh"
+#include "layers.cuh"
+
+using bq::bf16;
+using bq::GemmParams;
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;
+constexpr int kFeatures = 2048;
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched at run time: the library links only the static cudart)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
 }
+
+// 2-D bf16 K-major matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols]
+int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+              uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle swz = box_cols * sizeof(bf16) == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : box_cols * sizeof(bf16) == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                           : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+  return BQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+struct PwWeights {          // a GEMM's B operand + per-channel epilogue
+  int cin = 0, cout = 0, ktot = 0;
+  DevBuf w;                 // bf16 [cout][ktot]
+  DevBuf scale, shift;      // fp32 [cout]
+};
+struct SepWeights {
+  DevBuf dw;                // fp32 [9][cin]
+  PwWeights pw;
+};
+
+struct TensorIndex {
+  std::map<std::string, const bq_named_tensor*> by_name;
+  const bq_named_tensor* find(const std::string& n) const {
+    auto it = by_name.find(n);
+    return it == by_name.end() ? nullptr : it->second;
+  }
+};
+
+inline uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int upload(bq_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
+  int rc = bq_alloc(ctx, dst, bytes);
+  if (rc) return rc;
+  BQ_CUDA(ctx, cudaMemcpy(dst.p, src, bytes, cudaMemcpyHostToDevice));
+  return BQ_OK;
+}
+
+int need(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, std::initializer_list<int64_t> shape,
+         const bq_named_tensor** out) {
+  const bq_named_tensor* t = ti.find(name);
+  if (!t) return bq_fail(ctx, BQ_ERR_WEIGHTS, "missing weight tensor '%s'", name.c_str());
+  if (t->ndim != (int)shape.size()) return bq_fail(ctx, BQ_ERR_WEIGHTS, "'%s': expected %d dims, got %d", name.c_str(), (int)shape.size(), t->ndim);
+  int i = 0;
+  for (int64_t s : shape) {
+    if (t->shape[i] != s) return bq_fail(ctx, BQ_ERR_WEIGHTS, "'%s': dim %d is %lld, expected %lld", name.c_str(), i, (long long)t->shape[i], (long long)s);
+    ++i;
+  }
+  if (!t->data) return bq_fail(ctx, BQ_ERR_WEIGHTS, "'%s': null data", name.c_str());
+  *out = t;
+  return BQ_OK;
+}
+
+// BatchNorm (inference) -> y = x*scale + shift, eps = 1e-3 (Keras Xception)
+int load_bn(bq_ctx* ctx, const TensorIndex& ti, const std::string& bn, int c, PwWeights& w) {
+  const bq_named_tensor *g, *b, *m, *v;
+  int rc;
+  if ((rc = need(ctx, ti, bn + "/gamma", {c}, &g)) || (rc = need(ctx, ti, bn + "/beta", {c}, &b)) ||
+      (rc = need(ctx, ti, bn + "/moving_mean", {c}, &m)) || (rc = need(ctx, ti, bn + "/moving_variance", {c}, &v)))
+    return rc;
+  std::vector<float> sc(c), sh(c);
+  for (int i = 0; i < c; ++i) {
+    volatile float s = g->data[i] / sqrtf(v->data[i] + kBnEps);
+    volatile float ms = m->data[i] * s;
+    sc[i] = s;
+    sh[i] = b->data[i] - ms;
+  }
+  if ((rc = upload(ctx, w.scale, sc.data(), c * 4)) || (rc = upload(ctx, w.shift, sh.data(), c * 4))) return rc;
+  return BQ_OK;
+}
+
+// Keras kernel [kh,kw,cin,cout] (HWIO) -> bf16 [cout][kh*kw*cin]  (tap-major K, K-major rows)
+int load_conv_gemm(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, const std::string& var, int kh,
+                   int cin, int cout, PwWeights& w) {
+  const bq_named_tensor* k;
+  int rc = need(ctx, ti, name + "/" + var, {kh, kh, cin, cout}, &k);
+  if (rc) return rc;
+  const int ktot = kh * kh * cin;
+  std::vector<uint16_t> h((size_t)cout * ktot);
+  for (int t = 0; t < kh * kh; ++t)
+    for (int c = 0; c < cin; ++c)
+      for (int o = 0; o < cout; ++o)
+        h[(size_t)o * ktot + t * cin + c] = f32_to_bf16_rne(k->data[((size_t)t * cin + c) * cout + o]);
+  w.cin = cin; w.cout = cout; w.ktot = ktot;
+  if ((rc = upload(ctx, w.w, h.data(), h.size() * 2))) return rc;
+  return load_bn(ctx, ti, name + "_bn", cout, w);
+}
+
+int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int cin, int cout, PwWeights& w) {
+  const bq_named_tensor *k, *b;
+  int rc;
+  if ((rc = need(ctx, ti, name + "/kernel", {cin, cout}, &k)) || (rc = need(ctx, ti, name + "/bias", {cout}, &b))) return rc;
+  std::vector<uint16_t> h((size_t)cout * cin);
+  for (int c = 0; c < cin; ++c)
+    for (int o = 0; o < cout; ++o) h[(size_t)o * cin + c] = f32_to_bf16_rne(k->data[(size_t)c * cout + o]);
+  w.cin = cin; w.cout = cout; w.ktot = cin;
+  if ((rc = upload(ctx, w.w, h.data(), h.size() * 2))) return rc;
+  return upload(ctx, w.shift, b->data, cout * 4);   // scale stays null -> alpha
+}
+
+// ------------------------------------------------------------------------------------------------
+// execution plan
+// ------------------------------------------------------------------------------------------------
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP };
+
+struct Op {
+  OpKind kind;
+  int stage = 0;              // profiling bucket
+  std::string tag;            // non-empty: a named stage output (debug hook)
+  // generic tensor geometry (per tile)
+  const bf16* in = nullptr;
+  const bf16* in2 = nullptr;
+  bf16* out = nullptr;
+  int H = 0, W = 0, C = 0, Ho = 0, Wo = 0, Cout = 0;
+  int relu_in = 0, pad_top = 0, pad_left = 0;
+  const float* dw = nullptr;
+  // gemm
+  GemmParams gp;
+  int rows_per_tile = 0;      // M = rows_per_tile * batch
+  int blk_k = 64;
+  CUtensorMap ta, tb;
+};
+
+struct Arena {                // activation scratch: a handful of max-size buffers
+  DevBuf buf[5];
+  bf16* p(int i) { return (bf16*)buf[i].p; }
+};
+
+}  // namespace
+
+struct bq_model {
+  bq_ctx* ctx = nullptr;
+  bq_model_config cfg{};
+  bool weights_loaded = false;
+  bool use_simt = false;
+  int max_batch = 0;
+  int px = 299;
+
+  // weights
+  DevBuf conv1_w, conv1_scale, conv1_shift;    // fp32 [27][32], [32], [32]
+  PwWeights conv2;
+  std::map<std::string, std::unique_ptr<SepWeights>> sep;
+  std::map<std::string, std::unique_ptr<PwWeights>> res;
+  std::vector<std::unique_ptr<PwWeights>> hidden;
+  DevBuf w3, b3;                               // fp32 [width][classes], [classes]
+
+  // buffers
+  DevBuf tiles_dev;                            // uint8 staging [max_batch, px, px, 3]
+  DevBuf mean, inv_std;                        // fp32 [max_batch]
+  Arena arena;
+  DevBuf feat, feat_bf16;                      // [max_batch, 2048]
+  DevBuf h_act[2];                             // head activations: [max_batch * T, width] bf16 (ping-pong)
+  DevBuf a2;                                   // masked operand [max_batch * T, width]
+  DevBuf out_mean, out_std;                    // [max_batch, classes]
+  DevBuf masks_dev;
+  int head_T_cap = 0;
+
+  std::vector<Op> plan;
+  // head GEMM descriptors are rebuilt when T changes
+  struct HeadGemm { GemmParams gp; CUtensorMap ta, tb; };
+  std::vector<HeadGemm> head_gemms;
+  int head_T = -1;
+
+  bool profiling = false;
+  cudaEvent_t ev[9] = {};
+  float stage_ms[8] = {};
+};
+
+namespace {
+
+int same_pad_before(int h) {   // TF 'SAME', k=3, s=2
+  const int out = (h + 1) / 2;
+  int total = (out - 1) * 2 + 3 - h;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, int blk_k) {
+  bq_ctx* ctx = m->ctx;
+  if (gp.M <= 0) return BQ_OK;
+  if (m->use_simt) {
+    dim3 grid((gp.N + 31) / 32, (gp.M + 31) / 32), block(32, 32);
+    bq::gemm_simt_kernel<<<grid, block, 0, ctx->stream>>>(gp);
+    BQ_LAUNCH_CHECK(ctx);
+    return BQ_OK;
+  }
+  const int m_tiles = (gp.M + bq::sm100::kBM - 1) / bq::sm100::kBM;
+  const int n_tiles = (gp.N + gp.bn_box - 1) / gp.bn_box;
+  int grid = m_tiles * n_tiles;
+  if (grid > ctx->num_sms) grid = ctx->num_sms;
+  if (blk_k == 64) {
+    bq::sm100::gemm_tcgen05_kernel<64><<<grid, bq::sm100::kThreads, bq::sm100::SmemPlan<64>::kTotal, ctx->stream>>>(ta, tb, gp);
+  } else {
+    bq::sm100::gemm_tcgen05_kernel<32><<<grid, bq::sm100::kThreads, bq::sm100::SmemPlan<32>::kTotal, ctx->stream>>>(ta, tb, gp);
+  }
+  BQ_LAUNCH_CHECK(ctx);
+  return BQ_OK;
+}
+
+int bn_box_for(int n) {
+  int r = (n + 15) & ~15;
+  return r > 256 ? 256 : r;
+}
+
+// build a pointwise / dense GEMM op: A = [rows, K] activations at `a`, B = w, out = [rows, N]
+int make_gemm(bq_model* m, Op& op, const bf16* a, int rows_per_tile, const PwWeights& w, bf16* out, int relu,
+              const bf16* residual, float alpha = 1.0f) {
+  op.kind = OP_GEMM;
+  op.rows_per_tile = rows_per_tile;
+  op.blk_k = 64;
+  GemmParams& g = op.gp;
+  g = GemmParams();
+  g.M = rows_per_tile * m->max_batch;
+  g.N = w.cout;
+  g.K = w.ktot;
+  g.bn_box = bn_box_for(w.cout);
+  g.scale = (const float*)w.scale.p;
+  g.shift = (const float*)w.shift.p;
+  g.alpha = alpha;
+  g.residual = residual;
+  g.ldr = w.cout;
+  g.out = out;
+  g.ldc = w.cout;
+  g.relu = relu;
+  g.a_ptr = a; g.lda = w.ktot; g.a_rows = (long long)g.M;
+  g.b_ptr = (const bf16*)w.w.p; g.ldb = w.ktot;
+  int rc;
+  if ((rc = make_tmap(m->ctx, &op.ta, a, (uint64_t)g.M, (uint64_t)w.ktot, (uint64_t)w.ktot, 128, 64))) return rc;
+  if ((rc = make_tmap(m->ctx, &op.tb, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, g.bn_box, 64))) return rc;
+  return BQ_OK;
+}
+
+int build_plan(bq_model* m) {
+  bq_ctx* ctx = m->ctx;
+  const int B = m->max_batch;
+  const int px = m->px;
+  const int s1 = (px - 3) / 2 + 1;        // 149
+  const int s2 = s1 - 2;                  // 147
+  // arena: every buffer can hold the largest activation of the net: [B, s2, s2, 128]
+  const size_t max_elems = (size_t)B * s2 * s2 * 128;
+  for (auto& b : m->arena.buf) {
+    int rc = bq_alloc(ctx, b, max_elems * sizeof(bf16) + 1024);
+    if (rc) return rc;
+    BQ_CUDA(ctx, cudaMemset(b.p, 0, max_elems * sizeof(bf16) + 1024));
+  }
+  int rc;
+  if ((rc = bq_alloc(ctx, m->tiles_dev, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
+      (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
+      (rc = bq_alloc(ctx, m->feat_bf16, (size_t)B * kFeatures * 2)) ||
+      (rc = bq_alloc(ctx, m->out_mean, (size_t)B * m->cfg.n_classes * 4)) ||
+      (rc = bq_alloc(ctx, m->out_std, (size_t)B * m->cfg.n_classes * 4)))
+    return rc;
+
+  m->plan.clear();
+  Arena& A = m->arena;
+  int X = 0;                                  // arena index of the current block input
+  auto others = [&](int x, int (&t)[4]) { int k = 0; for (int i = 0; i < 5; ++i) if (i != x) t[k++] = i; };
+
+  // ---- block 1
+  { Op op; op.kind = OP_STATS; op.stage = 0; m->plan.push_back(op); }
+  { Op op; op.kind = OP_CONV1; op.stage = 0; op.out = A.p(0); op.H = px; op.Ho = s1; op.tag = "block1_conv1"; m->plan.push_back(op); }
+  {
+    Op op; op.kind = OP_GEMM; op.stage = 1; op.tag = "block1_conv2";
+    op.rows_per_tile = s1 * s1; op.blk_k = 32;
+    GemmParams& g = op.gp;
+    g.M = s1 * s1 * B; g.N = 64; g.K = 288; g.bn_box = 64;
+    g.scale = (const float*)m->conv2.scale.p; g.shift = (const float*)m->conv2.shift.p;
+    g.out = A.p(1); g.ldc = 64; g.relu = 1;
+    g.conv_mode = 1; g.in_w = s1; g.in_hw = s1 * s1; g.out_w = s2; g.out_h = s2; g.out_hw = s2 * s2;
+    g.a_ptr = A.p(0); g.lda = 32; g.a_rows = (long long)s1 * s1 * B;
+    g.b_ptr = (const bf16*)m->conv2.w.p; g.ldb = 288;
+    if ((rc = make_tmap(ctx, &op.ta, A.p(0), (uint64_t)s1 * s1 * B, 32, 32, 128, 32))) return rc;
+    if ((rc = make_tmap(ctx, &op.tb, m->conv2.w.p, 64, 288, 288, 64, 32))) return rc;
+    op.Ho = s2; op.Wo = s2; op.Cout = 64;
+    m->plan.push_back(op);
+  }
+  X = 1;
+  int H = s2, C = 64;
+
+  auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
+    Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
+    op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
+    m->plan.push_back(op);
+  };
+  auto add_gemm = [&](const bf16* a, int rows, const PwWeights& w, bf16* out, int relu, const bf16* resid, int stage,
+                      const char* tag, int h, int cout) -> int {
+    Op op; op.stage = stage;
+    int r = make_gemm(m, op, a, rows, w, out, relu, resid);
+    if (r) return r;
+    if (tag) op.tag = tag;
+    op.Ho = h; op.Wo = h; op.Cout = cout;
+    m->plan.push_back(op);
+    return BQ_OK;
+  };
+  // entry-style block with a strided 1x1 residual branch and a max-pool (blocks 2,3,4,13)
+  auto res_block = [&](int b, int cout1, int cout2, int relu_first, int stage) -> int {
+    int t[4]; others(X, t);
+    const int Ho = (H + 1) / 2;
+    const SepWeights& s1w = *m->sep.at("block" + std::to_string(b) + "_sepconv1");
+    const SepWeights& s2w = *m->sep.at("block" + std::to_string(b) + "_sepconv2");
+    const PwWeights& rw = *m->res.at("block" + std::to_string(b) + "_res");
+    { Op op; op.kind = OP_SUBSAMPLE; op.stage = stage; op.in = A.p(X); op.out = A.p(t[0]); op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = C; m->plan.push_back(op); }
+    int r;
+    if ((r = add_gemm(A.p(t[0]), Ho * Ho, rw, A.p(t[1]), 0, nullptr, stage, nullptr, Ho, cout2))) return r;   // res -> t1
+    add_dw(A.p(X), A.p(t[0]), H, C, relu_first, s1w, stage);
+    if ((r = add_gemm(A.p(t[0]), H * H, s1w.pw, A.p(t[2]), 1, nullptr, stage, nullptr, H, cout1))) return r;
+    add_dw(A.p(t[2]), A.p(t[0]), H, cout1, 0, s2w, stage);
+    if ((r = add_gemm(A.p(t[0]), H * H, s2w.pw, A.p(t[3]), 0, nullptr, stage, nullptr, H, cout2))) return r;
+    { Op op; op.kind = OP_POOLADD; op.stage = stage; op.in = A.p(t[3]); op.in2 = A.p(t[1]); op.out = A.p(X);
+      op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = cout2; op.Cout = cout2; op.pad_top = same_pad_before(H); op.pad_left = same_pad_before(H);
+      op.tag = "block" + std::to_string(b); m->plan.push_back(op); }
+    H = Ho; C = cout2;
+    return BQ_OK;
+  };
+  if ((rc = res_block(2, 128, 128, 0, 2)) || (rc = res_block(3, 256, 256, 1, 2)) || (rc = res_block(4, 728, 728, 1, 2))) return rc;
+  // ---- middle flow: 8 x (3 x (ReLU, sepconv, BN)) + identity
+  for (int b = 5; b <= 12; ++b) {
+    int t[4]; others(X, t);
+    const std::string pre = "block" + std::to_string(b) + "_sepconv";
+    const SepWeights &w1 = *m->sep.at(pre + "1"), &w2 = *m->sep.at(pre + "2"), &w3 = *m->sep.at(pre + "3");
+    add_dw(A.p(X), A.p(t[0]), H, C, 1, w1, 3);
+    if ((rc = add_gemm(A.p(t[0]), H * H, w1.pw, A.p(t[1]), 1, nullptr, 3, nullptr, H, C))) return rc;
+    add_dw(A.p(t[1]), A.p(t[0]), H, C, 0, w2, 3);
+    if ((rc = add_gemm(A.p(t[0]), H * H, w2.pw, A.p(t[1]), 1, nullptr, 3, nullptr, H, C))) return rc;
+    add_dw(A.p(t[1]), A.p(t[0]), H, C, 0, w3, 3);
+    const std::string tag = "block" + std::to_string(b);
+    if ((rc = add_gemm(A.p(t[0]), H * H, w3.pw, A.p(t[2]), 0, A.p(X), 3, tag.c_str(), H, C))) return rc;
+    X = t[2];
+  }
+  // ---- exit flow
+  if ((rc = res_block(13, 728, 1024, 1, 4))) return rc;
+  {
+    int t[4]; others(X, t);
+    const SepWeights &w1 = *m->sep.at("block14_sepconv1"), &w2 = *m->sep.at("block14_sepconv2");
+    add_dw(A.p(X), A.p(t[0]), H, C, 0, w1, 4);
+    if ((rc = add_gemm(A.p(t[0]), H * H, w1.pw, A.p(t[1]), 1, nullptr, 4, nullptr, H, 1536))) return rc;
+    add_dw(A.p(t[1]), A.p(t[0]), H, 1536, 0, w2, 4);
+    if ((rc = add_gemm(A.p(t[0]), H * H, w2.pw, A.p(t[2]), 1, nullptr, 4, "block14", H, kFeatures))) return rc;
+    Op op; op.kind = OP_GAP; op.stage = 4; op.in = A.p(t[2]); op.H = H; op.W = H; op.C = kFeatures; m->plan.push_back(op);
+  }
+  return BQ_OK;
+}
+
+int run_op(bq_model* m, Op& op, int nb) {
+  bq_ctx* ctx = m->ctx;
+  const int px = m->px;
+  auto grid1d = [&](int64_t total) {
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->num_sms * 32;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+  };
+  switch (op.kind) {
+    case OP_STATS:
+      bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (int64_t)px * px * 3,
+                                                        (float*)m->mean.p, (float*)m->inv_std.p);
+      break;
+    case OP_CONV1: {
+      dim3 grid((op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, (op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, nb);
+      bq::conv1_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (const float*)m->mean.p,
+                                                     (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
+                                                     (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
+                                                     op.out, px, op.Ho);
+      break;
+    }
+    case OP_GEMM: {
+      GemmParams g = op.gp;
+      g.M = op.rows_per_tile * nb;
+      g.a_rows = (long long)op.rows_per_tile * m->max_batch;
+      return launch_gemm(m, g, op.ta, op.tb, op.blk_k);
+    }
+    case OP_DW:
+      bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
+          op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
+      break;
+    case OP_POOLADD:
+      bq::maxpool_add_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
+          op.in, op.in2, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left);
+      break;
+    case OP_SUBSAMPLE:
+      bq::subsample2_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
+          op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C);
+      break;
+    case OP_GAP:
+      bq::gap_kernel<<<grid1d((int64_t)nb * op.C), 256, 0, ctx->stream>>>(op.in, (float*)m->feat.p,
+                                                                           (bf16*)m->feat_bf16.p, nb, op.H * op.W, op.C);
+      break;
+  }
+  BQ_LAUNCH_CHECK(ctx);
+  return BQ_OK;
+}
+
+int stage_tiles(bq_model* m, const uint8_t* tiles, int nb) {
+  bq_ctx* ctx = m->ctx;
+  const size_t bytes = (size_t)nb * m->px * m->px * 3;
+  BQ_CUDA(ctx, cudaMemcpyAsync(m->tiles_dev.p, tiles, bytes, cudaMemcpyDefault, ctx->stream));
+  return BQ_OK;
+}
+
+int run_backbone(bq_model* m, int nb, const std::string* stop_tag, const Op** stopped) {
+  int cur_stage = -1;
+  for (auto& op : m->plan) {
+    if (m->profiling && op.stage != cur_stage) {
+      cudaEventRecord(m->ev[op.stage], m->ctx->stream);
+      cur_stage = op.stage;
+    }
+    int rc = run_op(m, op, nb);
+    if (rc) return rc;
+    if (stop_tag && op.tag == *stop_tag) { if (stopped) *stopped = &op; return BQ_OK; }
+  }
+  if (m->profiling) cudaEventRecord(m->ev[5], m->ctx->stream);
+  return BQ_OK;
+}
+
+// (re)build head GEMM descriptors for T samples
+int prepare_head(bq_model* m, int T) {
+  bq_ctx* ctx = m->ctx;
+  if (m->head_T == T) return BQ_OK;
+  const int B = m->max_batch, Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers;
+  int rc;
+  const size_t rows = (size_t)B * T;
+  if (T > m->head_T_cap) {
+    BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& h : m->h_act) { h.release(); if ((rc = bq_alloc(ctx, h, rows * Wd * 2 + 1024))) return rc; }
+    m->a2.release();
+    if ((rc = bq_alloc(ctx, m->a2, rows * Wd * 2 + 1024))) return rc;
+    m->head_T_cap = T;
+  }
+  m->head_gemms.clear();
+  m->head_gemms.resize(Hn);
+  const float inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+  for (int i = 0; i < Hn; ++i) {
+    Op op;
+    const PwWeights& w = *m->hidden[i];
+    // layer 0: A = pooled features [B, 2048] -> h_act[0] [B, Wd]; layer i>0: A = masked operand [B*T, Wd]
+    const bf16* a = i == 0 ? (const bf16*)m->feat_bf16.p : (const bf16*)m->a2.p;
+    bf16* out = (bf16*)m->h_act[i & 1].p;
+    m->max_batch = i == 0 ? B : B * T;   // make_gemm sizes M = rows_per_tile * max_batch
+    rc = make_gemm(m, op, a, 1, w, out, 1, nullptr, i == 0 ? 1.0f : inv_keep);
+    m->max_batch = B;
+    if (rc) return rc;
+    m->head_gemms[i].gp = op.gp;
+    m->head_gemms[i].ta = op.ta;
+    m->head_gemms[i].tb = op.tb;
+  }
+  m->head_T = T;
+  return BQ_OK;
+}
+
+int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, const uint8_t* masks_dev) {
+  bq_ctx* ctx = m->ctx;
+  const int Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers, NC = m->cfg.n_classes;
+  const uint32_t thresh = (uint32_t)floor((double)m->cfg.dropout * 4294967296.0);
+  int rc = prepare_head(m, T);
+  if (rc) return rc;
+  auto grid1d = [&](int64_t total) {
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->num_sms * 32;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+  };
+  for (int i = 0; i < Hn; ++i) {
+    auto& hg = m->head_gemms[i];
+    GemmParams g = hg.gp;
+    if (i == 0) {
+      g.M = nb;
+    } else {
+      // dropout site i: masked copy of the previous activation, one row per (tile, sample)
+      const bf16* src = (const bf16*)m->h_act[(i - 1) & 1].p;
+      const int per_sample = i >= 2;     // layer-1 input is per tile, deeper inputs are already per sample
+      if (per_sample) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers > 2 is not supported yet");
+      bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (Wd / 4)), 256, 0, ctx->stream>>>(
+          src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, Hn, i - 1);
+      BQ_LAUNCH_CHECK(ctx);
+      g.M = nb * T;
+    }
+    if ((rc = launch_gemm(m, g, hg.ta, hg.tb, 64))) return rc;
+  }
+  const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
+  const int Teff = Hn == 1 ? 1 : T;
+  if (Hn == 1) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers == 1 is not supported yet");
+  const float inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+  bq::head_final_kernel<<<nb, 256, (size_t)T * NC * sizeof(float), ctx->stream>>>(
+      last, (const float*)m->w3.p, (const float*)m->b3.p, Teff, Wd, NC, inv_keep, 1, seed, tile_base, Hn, thresh,
+      masks_dev, Hn, Hn - 1, (float*)m->out_mean.p, (float*)m->out_std.p);
+  BQ_LAUNCH_CHECK(ctx);
+  return BQ_OK;
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
+  if (!ctx) return BQ_ERR_ARG;
+  if (!cfg || !out) return bq_fail(ctx, BQ_ERR_ARG, "bq_model_create: null argument");
+  if (cfg->tile_px != 299) return bq_fail(ctx, BQ_ERR_ARG, "tile_px must be 299 (hp.py:5), got %d", cfg->tile_px);
+  if (cfg->hidden_layers != 2) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers must be 2 (hp.py:21), got %d", cfg->hidden_layers);
+  if (cfg->hidden_width <= 0 || cfg->hidden_width % 64) return bq_fail(ctx, BQ_ERR_ARG, "hidden_width must be a positive multiple of 64");
+  if (cfg->n_classes < 2 || cfg->n_classes > bq::kMaxClasses) return bq_fail(ctx, BQ_ERR_ARG, "n_classes must be in [2,8]");
+  if (!(cfg->dropout >= 0.f && cfg->dropout < 1.f)) return bq_fail(ctx, BQ_ERR_ARG, "dropout must be in [0,1)");
+  if (cfg->max_batch < 1 || cfg->max_batch > 512) return bq_fail(ctx, BQ_ERR_ARG, "max_batch must be in [1,512]");
+  BQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  bq_model* m = new bq_model();
+  m->ctx = ctx;
+  m->cfg = *cfg;
+  m->max_batch = cfg->max_batch;
+  m->px = cfg->tile_px;
+  const char* g = getenv("BQ_GEMM");
+  m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
+  for (auto& e : m->ev) cudaEventCreate(&e);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan<64>::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan<32>::kTotal);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete m; return bq_fail(ctx, BQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  *out = m;
+  return BQ_OK;
+}
+
+void bq_model_destroy(bq_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  delete m;
+}
+
+int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n_tensors) {
+  if (!m) return BQ_ERR_ARG;
+  bq_ctx* ctx = m->ctx;
+  if (!tensors || n_tensors <= 0) return bq_fail(ctx, BQ_ERR_ARG, "bq_model_load_weights: no tensors");
+  BQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  TensorIndex ti;
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].name) ti.by_name[tensors[i].name] = &tensors[i];
+  int rc;
+  // block1_conv1: fp32 [3,3,3,32] used as-is ([27][32]) by the fused decode/standardise/conv kernel
+  {
+    const bq_named_tensor* k;
+    if ((rc = need(ctx, ti, "block1_conv1/kernel", {3, 3, 3, 32}, &k))) return rc;
+    if ((rc = upload(ctx, m->conv1_w, k->data, 27 * 32 * 4))) return rc;
+    PwWeights tmp;
+    if ((rc = load_bn(ctx, ti, "block1_conv1_bn", 32, tmp))) return rc;
+    m->conv1_scale.release(); m->conv1_shift.release();
+    std::swap(m->conv1_scale.p, tmp.scale.p); std::swap(m->conv1_scale.bytes, tmp.scale.bytes); std::swap(m->conv1_scale.owned, tmp.scale.owned);
+    std::swap(m->conv1_shift.p, tmp.shift.p); std::swap(m->conv1_shift.bytes, tmp.shift.bytes); std::swap(m->conv1_shift.owned, tmp.shift.owned);
+  }
+  if ((rc = load_conv_gemm(ctx, ti, "block1_conv2", "kernel", 3, 32, 64, m->conv2))) return rc;
+  auto load_sep = [&](const std::string& name, int cin, int cout) -> int {
+    std::unique_ptr<SepWeights> s(new SepWeights());
+    const bq_named_tensor* d;
+    int r;
+    if ((r = need(ctx, ti, name + "/depthwise_kernel", {3, 3, cin, 1}, &d))) return r;
+    if ((r = upload(ctx, s->dw, d->data, (size_t)9 * cin * 4))) return r;
+    if ((r = load_conv_gemm(ctx, ti, name, "pointwise_kernel", 1, cin, cout, s->pw))) return r;
+    m->sep[name] = std::move(s);
+    return BQ_OK;
+  };
+  auto load_res = [&](const std::string& name, int cin, int cout) -> int {
+    std::unique_ptr<PwWeights> w(new PwWeights());
+    int r = load_conv_gemm(ctx, ti, name, "kernel", 1, cin, cout, *w);
+    if (r) return r;
+    m->res[name] = std::move(w);
+    return BQ_OK;
+  };
+  const int entry[3][3] = {{2, 64, 128}, {3, 128, 256}, {4, 256, 728}};
+  for (auto& e : entry) {
+    const std::string b = "block" + std::to_string(e[0]);
+    if ((rc = load_res(b + "_res", e[1], e[2])) || (rc = load_sep(b + "_sepconv1", e[1], e[2])) ||
+        (rc = load_sep(b + "_sepconv2", e[2], e[2])))
+      return rc;
+  }
+  for (int b = 5; b <= 12; ++b)
+    for (int i = 1; i <= 3; ++i)
+      if ((rc = load_sep("block" + std::to_string(b) + "_sepconv" + std::to_string(i), 728, 728))) return rc;
+  if ((rc = load_res("block13_res", 728, 1024)) || (rc = load_sep("block13_sepconv1", 728, 728)) ||
+      (rc = load_sep("block13_sepconv2", 728, 1024)) || (rc = load_sep("block14_sepconv1", 1024, 1536)) ||
+      (rc = load_sep("block14_sepconv2", 1536, 2048)))
+    return rc;
+  // head
+  m->hidden.clear();
+  int cin = kFeatures;
+  for (int i = 0; i < m->cfg.hidden_layers; ++i) {
+    std::unique_ptr<PwWeights> w(new PwWeights());
+    if ((rc = load_dense(ctx, ti, "hidden_" + std::to_string(i), cin, m->cfg.hidden_width, *w))) return rc;
+    m->hidden.push_back(std::move(w));
+    cin = m->cfg.hidden_width;
+  }
+  {
+    const bq_named_tensor *k, *b;
+    if ((rc = need(ctx, ti, "prelogits/kernel", {cin, m->cfg.n_classes}, &k)) ||
+        (rc = need(ctx, ti, "prelogits/bias", {m->cfg.n_classes}, &b)))
+      return rc;
+    if ((rc = upload(ctx, m->w3, k->data, (size_t)cin * m->cfg.n_classes * 4)) ||
+        (rc = upload(ctx, m->b3, b->data, m->cfg.n_classes * 4)))
+      return rc;
+  }
+  if ((rc = build_plan(m))) return rc;
+  m->head_T = -1;
+  m->weights_loaded = true;
+  return BQ_OK;
+}
+
+int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint64_t seed, uint64_t tile_index_base,
+                  const uint8_t* masks, float* mean, float* std, float* features) {
+  if (!m) return BQ_ERR_ARG;
+  bq_ctx* ctx = m->ctx;
+  if (!m->weights_loaded) return bq_fail(ctx, BQ_ERR_STATE, "bq_predict_uq: weights not loaded");
+  if (n < 0 || T < 1 || T > 4096 || (n > 0 && (!tiles || !mean || !std)))
+    return bq_fail(ctx, BQ_ERR_ARG, "bq_predict_uq: bad argument");
+  BQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int B = m->max_batch, NC = m->cfg.n_classes, Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers;
+  const size_t tile_bytes = (size_t)m->px * m->px * 3;
+  const size_t mask_per_tile = (size_t)T * Hn * Wd;
+  const bool masks_on_dev = masks && bq_is_device_ptr(masks);
+  if (masks && !masks_on_dev) {
+    int rc = bq_alloc(ctx, m->masks_dev, (size_t)B * mask_per_tile);
+    if (rc) return rc;
+  }
+  if (m->profiling) for (auto& s : m->stage_ms) s = 0.f;
+  for (int64_t i0 = 0; i0 < n; i0 += B) {
+    const int nb = (int)((n - i0 < B) ? (n - i0) : B);
+    int rc;
+    if ((rc = stage_tiles(m, tiles + (size_t)i0 * tile_bytes, nb))) return rc;
+    const uint8_t* mdev = nullptr;
+    if (masks) {
+      if (masks_on_dev) mdev = masks + (size_t)i0 * mask_per_tile;
+      else {
+        BQ_CUDA(ctx, cudaMemcpyAsync(m->masks_dev.p, masks + (size_t)i0 * mask_per_tile, (size_t)nb * mask_per_tile,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        mdev = (const uint8_t*)m->masks_dev.p;
+      }
+    }
+    if ((rc = run_backbone(m, nb, nullptr, nullptr))) return rc;
+    if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0, mdev))) return rc;
+    if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
+    if ((rc = bq_from_device(ctx, mean + (size_t)i0 * NC, m->out_mean.p, (size_t)nb * NC * 4)) ||
+        (rc = bq_from_device(ctx, std + (size_t)i0 * NC, m->out_std.p, (size_t)nb * NC * 4)))
+      return rc;
+    if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
+      return rc;
+    if (m->profiling) {
+      BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int s = 0; s < 6; ++s) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->ev[s], m->ev[s + 1]) == cudaSuccess) m->stage_ms[s] += ms;
+      }
+    }
+  }
+  BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BQ_OK;
+}
+
+int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const char* stage, float* out,
+                         int64_t out_capacity, int64_t out_shape[4]) {
+  if (!m) return BQ_ERR_ARG;
+  bq_ctx* ctx = m->ctx;
+  if (!m->weights_loaded) return bq_fail(ctx, BQ_ERR_STATE, "weights not loaded");
+  if (!tiles || !stage || !out || !out_shape || n < 1 || n > m->max_batch)
+    return bq_fail(ctx, BQ_ERR_ARG, "bq_model_debug_stage: bad argument (n must be <= max_batch)");
+  BQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = stage_tiles(m, tiles, (int)n))) return rc;
+  const std::string tag(stage);
+  const Op* op = nullptr;
+  const bool prof = m->profiling;
+  m->profiling = false;
+  rc = run_backbone(m, (int)n, &tag, &op);
+  m->profiling = prof;
+  if (rc) return rc;
+  if (!op) return bq_fail(ctx, BQ_ERR_ARG, "unknown stage '%s'", stage);
+  const bf16* src = op->kind == OP_GEMM ? op->gp.out : op->out;
+  const int64_t h = op->Ho, w = op->kind == OP_CONV1 ? op->Ho : op->Wo, c = op->kind == OP_CONV1 ? 32 : op->Cout;
+  const int64_t total = n * h * w * c;
+  out_shape[0] = n; out_shape[1] = h; out_shape[2] = w; out_shape[3] = c;
+  if (total > out_capacity) return bq_fail(ctx, BQ_ERR_ARG, "output buffer too small: need %lld floats", (long long)total);
+  void* scr = nullptr;
+  if ((rc = bq_scratch(ctx, total * 4, &scr))) return rc;
+  bf16_to_f32_kernel<<<1024, 256, 0, ctx->stream>>>(src, (float*)scr, total);
+  BQ_LAUNCH_CHECK(ctx);
+  if ((rc = bq_from_device(ctx, out, scr, total * 4))) return rc;
+  BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BQ_OK;
+}
+
+int bq_model_set_profiling(bq_model* m, int enabled) {
+  if (!m) return BQ_ERR_ARG;
+  m->profiling = enabled != 0;
+  return BQ_OK;
+}
+
+int bq_model_last_stage_ms(bq_model* m, float ms[8]) {
+  if (!m || !ms) return BQ_ERR_ARG;
+  for (int i = 0; i < 8; ++i) ms[i] = m->stage_ms[i];
+  return BQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""GPU tier: Xception-UQ MC-dropout inference (CUDA, through the C ABI) against the CPU oracle
+(oracle/xception_uq.py -- restated from Slideflow/Keras, parity with TensorFlow itself unpinned).
+
+Tolerances (stated per north_star):
+  * vs the bf16-emulated oracle (same rounding points as the CUDA path, fp32 accumulation in a
+    different order): backbone stages  max|d| <= 3e-2 * max|ref|,  mean|d| <= 4e-3 * mean|ref|;
+    per-tile mean / std with INJECTED dropout masks: |d| <= 4e-3 absolute;
+  * vs the fp32 oracle (the reference's arithmetic type): mean / std |d| <= 1.5e-2 absolute;
+  * independently sampled masks: statistical tolerance 6 * std / sqrt(T) on the mean.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import synth, xception_uq as X
+
+pytestmark = pytest.mark.gpu
+
+N_TILES = 6
+T = 30
+SEED = 1234
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return X.make_weights(seed=1)
+
+
+@pytest.fixture(scope="module")
+def tiles():
+    return synth.tiles_u8(N_TILES, seed=0, n_slides=3)
+
+
+@pytest.fixture(scope="module")
+def iface(weights):
+    from biscuit_b200.uq import UncertaintyInterface
+    return UncertaintyInterface(weights, max_batch=4)     # < N_TILES: exercises a partial micro-batch
+
+
+@pytest.fixture(scope="module")
+def oracle_bf16(weights, tiles):
+    o = X.XceptionUQOracle(weights, emulate_bf16=True)
+    stages = {}
+    import torch
+    with torch.no_grad():
+        feats = o.backbone(tiles, stages=stages)
+    return o, stages, feats
+
+
+STAGES = ["block1_conv1", "block1_conv2", "block2", "block3", "block4", "block5", "block8", "block12",
+          "block13", "block14"]
+
+
+@pytest.mark.parametrize("stage", STAGES)
+def test_backbone_stage_parity(iface, tiles, oracle_bf16, stage):
+    _, stages, _ = oracle_bf16
+    got = iface.debug_stage(tiles[:4], stage)
+    ref = stages[stage][:4]
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    d = np.abs(got - ref)
+    stats = dict(max_d=float(d.max()), max_ref=float(np.abs(ref).max()), mean_d=float(d.mean()),
+                 mean_ref=float(np.abs(ref).mean()))
+    print(stage, stats)
+    assert d.max() <= 3e-2 * np.abs(ref).max(), stats
+    assert d.mean() <= 4e-3 * np.abs(ref).mean(), stats
+
+
+def test_features_and_uq_with_injected_masks(iface, tiles, oracle_bf16, weights):
+    o, _, feats_ref = oracle_bf16
+    masks = X.keep_masks(N_TILES, T, 1024, 0.1, SEED)
+    mean, std, feats = iface.predict(tiles, T=T, masks=masks, return_features=True)
+    fr = feats_ref.numpy()
+    assert np.abs(feats - fr).max() <= 3e-2 * np.abs(fr).max()
+    m_ref, s_ref = o.predict_uq(tiles, T=T, masks=masks)
+    print("bf16-tier  d_mean", np.abs(mean - m_ref).max(), "d_std", np.abs(std - s_ref).max())
+    assert np.abs(mean - m_ref).max() <= 4e-3
+    assert np.abs(std - s_ref).max() <= 4e-3
+    assert np.allclose(mean.sum(1), 1.0, atol=1e-5)
+    # fp32 oracle = the reference's arithmetic type
+    o32 = X.XceptionUQOracle(weights, emulate_bf16=False)
+    m32, s32 = o32.predict_uq(tiles, T=T, masks=masks)
+    print("fp32-tier  d_mean", np.abs(mean - m32).max(), "d_std", np.abs(std - s32).max())
+    assert np.abs(mean - m32).max() <= 1.5e-2
+    assert np.abs(std - s32).max() <= 1.5e-2
+    # the outputs are not degenerate (otherwise the comparison above would be vacuous)
+    assert std[:, 1].min() > 1e-3 and 0.02 < mean[:, 1].min() and mean[:, 1].max() < 0.98
+
+
+def test_philox_stream_equals_oracle_masks(iface, tiles):
+    """counter-based Philox4x32-10 in the kernels == oracle.keep_masks: identical outputs bit for bit"""
+    for base in (0, 5, (1 << 32) + 3):
+        masks = X.keep_masks(N_TILES, T, 1024, 0.1, SEED, tile_index_base=base)
+        a = iface.predict(tiles, T=T, masks=masks)
+        b = iface.predict(tiles, T=T, seed=SEED, tile_index_base=base)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_reference_schedule_equivalence(weights, tiles):
+    """the reference runs T FULL forward passes; one backbone pass + T head passes is identical"""
+    o = X.XceptionUQOracle(weights, emulate_bf16=False)
+    masks = X.keep_masks(2, 3, 1024, 0.1, 7)
+    a = o.predict_uq(tiles[:2], T=3, masks=masks, reference_schedule=True)
+    b = o.predict_uq(tiles[:2], T=3, masks=masks, reference_schedule=False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_independent_masks_statistical_tolerance(iface, tiles):
+    m1, s1 = iface.predict(tiles, T=100, seed=1)
+    m2, s2 = iface.predict(tiles, T=100, seed=2)
+    assert not np.array_equal(m1, m2)
+    tol = 6.0 * np.maximum(s1, s2)[:, 1] / np.sqrt(100.0) + 1e-4
+    assert (np.abs(m1[:, 1] - m2[:, 1]) <= tol).all(), (m1[:, 1], m2[:, 1], tol)
+    assert np.abs(s1[:, 1] - s2[:, 1]).max() <= 0.5 * np.maximum(s1, s2)[:, 1].max()
+
+
+def test_micro_batch_and_shard_invariance(weights, tiles, iface):
+    """results do not depend on the micro-batch size nor on how tiles are sharded (tile_index_base)"""
+    from biscuit_b200.uq import UncertaintyInterface
+    big = UncertaintyInterface(weights, max_batch=8)
+    a = iface.predict(tiles, T=T, seed=SEED)
+    b = big.predict(tiles, T=T, seed=SEED)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    lo = big.predict(tiles[:2], T=T, seed=SEED, tile_index_base=0)
+    hi = big.predict(tiles[2:], T=T, seed=SEED, tile_index_base=2)
+    assert np.array_equal(np.concatenate([lo[0], hi[0]]), a[0])
+    assert np.array_equal(np.concatenate([lo[1], hi[1]]), a[1])
+    big.close()
+
+
+def test_sample_sweep_and_call_surface(iface, tiles):
+    for t in (1, 10, 30, 100):
+        mean, std = iface.predict(tiles[:3], T=t, seed=3)
+        assert np.isfinite(mean).all() and np.isfinite(std).all()
+        if t == 1:
+            assert (std == 0).all()
+    logits, unc = iface(tiles[:2])                     # reference call surface (results.py:257)
+    assert logits.shape == (2, 2) and unc.shape == (2, 1)
+
+
+def test_device_resident_tiles(iface, tiles):
+    import torch
+    d = torch.from_numpy(tiles).cuda()
+    a = iface.predict(d, T=T, seed=SEED)
+    b = iface.predict(tiles, T=T, seed=SEED)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_simt_debug_path_agrees():
+    """BQ_GEMM=simt (plain CUDA-core GEMM, debug only) vs the default tcgen05 path: same bf16 inputs, fp32
+    accumulation in a different order"""
+    code = (
+        "import numpy as np, sys\n"
+        "from oracle import synth, xception_uq as X\n"
+        "from biscuit_b200.uq import UncertaintyInterface\n"
+        "i = UncertaintyInterface(X.make_weights(seed=1), max_batch=2)\n"
+        "m, s, f = i.predict(synth.tiles_u8(2, seed=0), T=10, seed=5, return_features=True)\n"
+        "np.save(sys.argv[1], np.concatenate([m.ravel(), s.ravel(), f.ravel()]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("simt", "tcgen05"):
+        path = f"/tmp/bq_{mode}.npy"
+        env = dict(os.environ, BQ_GEMM=mode, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
+        outs.append(np.load(path))
+    a, b = outs
+    print("simt vs tcgen05: max d (mean/std)", np.abs(a[:8] - b[:8]).max(), "features", np.abs(a[8:] - b[8:]).max())
+    assert np.abs(a[:8] - b[:8]).max() <= 3e-3
+    assert np.abs(a[8:] - b[8:]).max() <= 2e-2 * np.abs(a[8:]).max()
