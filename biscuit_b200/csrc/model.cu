@@ -225,9 +225,15 @@ struct bq_model {
   std::vector<HeadGemm> head_gemms;
   int head_T = -1;
 
-  bool profiling = false;
+  int profiling = 0;                           // 0 off, 1 per stage, 2 per kernel family
   cudaEvent_t ev[9] = {};
   float stage_ms[8] = {};
+  // per-kernel-family accounting (profiling == 2): event pair around every launch
+  std::vector<cudaEvent_t> kev;
+  struct KRec { int kind; double flops, bytes; };
+  std::vector<KRec> krec;
+  double k_ms[BQ_PROFILE_KINDS] = {}, k_flops[BQ_PROFILE_KINDS] = {}, k_bytes[BQ_PROFILE_KINDS] = {};
+  int64_t k_launches[BQ_PROFILE_KINDS] = {};
 };
 
 namespace {
@@ -237,6 +243,31 @@ int same_pad_before(int h) {   // TF 'SAME', k=3, s=2
   int total = (out - 1) * 2 + 3 - h;
   if (total < 0) total = 0;
   return total / 2;
+}
+
+// profiling == 2: event pair around one launch, tagged with its kernel family and algorithmic work
+struct KScope {
+  bq_model* m; bool on;
+  KScope(bq_model* m_, int kind, double flops, double bytes) : m(m_), on(m_->profiling == 2) {
+    if (!on) return;
+    const size_t i = m->krec.size();
+    while (m->kev.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); m->kev.push_back(e); }
+    m->krec.push_back({kind, flops, bytes});
+    cudaEventRecord(m->kev[2 * i], m->ctx->stream);
+  }
+  ~KScope() { if (on) cudaEventRecord(m->kev[2 * (m->krec.size() - 1) + 1], m->ctx->stream); }
+};
+
+void kprofile_collect(bq_model* m) {
+  if (m->profiling != 2) return;
+  cudaStreamSynchronize(m->ctx->stream);
+  for (size_t i = 0; i < m->krec.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->kev[2 * i], m->kev[2 * i + 1]) != cudaSuccess) continue;
+    const int k = m->krec[i].kind;
+    m->k_ms[k] += ms; m->k_flops[k] += m->krec[i].flops; m->k_bytes[k] += m->krec[i].bytes; m->k_launches[k]++;
+  }
+  m->krec.clear();
 }
 
 int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, int blk_k) {
@@ -413,12 +444,16 @@ int run_op(bq_model* m, Op& op, int nb) {
     const int64_t cap = (int64_t)ctx->num_sms * 32;
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
   };
+  const double act = 2.0;   // bytes per bf16 activation element
   switch (op.kind) {
-    case OP_STATS:
+    case OP_STATS: {
+      KScope ks(m, BQ_K_STATS, 0, (double)nb * px * px * 3);
       bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (int64_t)px * px * 3,
                                                         (float*)m->mean.p, (float*)m->inv_std.p);
       break;
+    }
     case OP_CONV1: {
+      KScope ks(m, BQ_K_CONV1, 2.0 * nb * op.Ho * op.Ho * 27 * 32, (double)nb * px * px * 3 + act * nb * op.Ho * op.Ho * 32);
       dim3 grid((op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, (op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, nb);
       bq::conv1_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (const float*)m->mean.p,
                                                      (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
@@ -430,24 +465,36 @@ int run_op(bq_model* m, Op& op, int nb) {
       GemmParams g = op.gp;
       g.M = op.rows_per_tile * nb;
       g.a_rows = (long long)op.rows_per_tile * m->max_batch;
+      const double rows_out = g.conv_mode ? (double)nb * g.out_hw : (double)g.M;
+      const double kin = g.conv_mode ? g.K / 9 : g.K;
+      KScope ks(m, g.conv_mode ? BQ_K_GEMM_CONV2 : BQ_K_GEMM_PW, 2.0 * rows_out * g.N * g.K,
+                act * ((double)g.M * kin + rows_out * g.N * (g.residual ? 2 : 1) + (double)g.N * g.K));
       return launch_gemm(m, g, op.ta, op.tb, op.blk_k);
     }
-    case OP_DW:
+    case OP_DW: {
+      KScope ks(m, BQ_K_DW, 2.0 * 9 * nb * op.H * op.W * op.C, 2 * act * nb * op.H * op.W * op.C);
       bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
           op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
       break;
-    case OP_POOLADD:
+    }
+    case OP_POOLADD: {
+      KScope ks(m, BQ_K_POOLADD, 0, act * nb * op.C * ((double)op.H * op.W + 2.0 * op.Ho * op.Wo));
       bq::maxpool_add_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
           op.in, op.in2, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left);
       break;
-    case OP_SUBSAMPLE:
+    }
+    case OP_SUBSAMPLE: {
+      KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.Ho * op.Wo * op.C);
       bq::subsample2_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
           op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C);
       break;
-    case OP_GAP:
+    }
+    case OP_GAP: {
+      KScope ks(m, BQ_K_GAP, 0, act * nb * op.H * op.W * op.C + 6.0 * nb * op.C);
       bq::gap_kernel<<<grid1d((int64_t)nb * op.C), 256, 0, ctx->stream>>>(op.in, (float*)m->feat.p,
                                                                            (bf16*)m->feat_bf16.p, nb, op.H * op.W, op.C);
       break;
+    }
   }
   BQ_LAUNCH_CHECK(ctx);
   return BQ_OK;
@@ -531,17 +578,22 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
       const bf16* src = (const bf16*)m->h_act[(i - 1) & 1].p;
       const int per_sample = i >= 2;     // layer-1 input is per tile, deeper inputs are already per sample
       if (per_sample) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers > 2 is not supported yet");
-      bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (Wd / 4)), 256, 0, ctx->stream>>>(
-          src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, Hn, i - 1);
+      {
+        KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * Wd + 2.0 * nb * T * Wd);
+        bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (Wd / 4)), 256, 0, ctx->stream>>>(
+            src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, Hn, i - 1);
+      }
       BQ_LAUNCH_CHECK(ctx);
       g.M = nb * T;
     }
+    KScope ks(m, BQ_K_HEAD_GEMM, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
     if ((rc = launch_gemm(m, g, hg.ta, hg.tb, 64))) return rc;
   }
   const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
   const int Teff = Hn == 1 ? 1 : T;
   if (Hn == 1) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers == 1 is not supported yet");
   const float inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+  KScope ks(m, BQ_K_HEAD_FINAL, 2.0 * nb * T * Wd * NC, 2.0 * nb * T * Wd + 8.0 * nb * NC);
   bq::head_final_kernel<<<nb, 256, (size_t)T * NC * sizeof(float), ctx->stream>>>(
       last, (const float*)m->w3.p, (const float*)m->b3.p, Teff, Wd, NC, inv_keep, 1, seed, tile_base, Hn, thresh,
       masks_dev, Hn, Hn - 1, (float*)m->out_mean.p, (float*)m->out_std.p);
@@ -594,6 +646,7 @@ void bq_model_destroy(bq_model* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : m->kev) cudaEventDestroy(e);
   delete m;
 }
 
@@ -690,6 +743,8 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
     if (rc) return rc;
   }
   if (m->profiling) for (auto& s : m->stage_ms) s = 0.f;
+  if (m->profiling == 2)
+    for (int k = 0; k < BQ_PROFILE_KINDS; ++k) { m->k_ms[k] = m->k_flops[k] = m->k_bytes[k] = 0; m->k_launches[k] = 0; }
   for (int64_t i0 = 0; i0 < n; i0 += B) {
     const int nb = (int)((n - i0 < B) ? (n - i0) : B);
     int rc;
@@ -711,6 +766,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
       return rc;
     if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
       return rc;
+    kprofile_collect(m);
     if (m->profiling) {
       BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       for (int s = 0; s < 6; ++s) {
@@ -735,8 +791,8 @@ int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const cha
   if ((rc = stage_tiles(m, tiles, (int)n))) return rc;
   const std::string tag(stage);
   const Op* op = nullptr;
-  const bool prof = m->profiling;
-  m->profiling = false;
+  const int prof = m->profiling;
+  m->profiling = 0;
   rc = run_backbone(m, (int)n, &tag, &op);
   m->profiling = prof;
   if (rc) return rc;
@@ -757,7 +813,16 @@ int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const cha
 
 int bq_model_set_profiling(bq_model* m, int enabled) {
   if (!m) return BQ_ERR_ARG;
-  m->profiling = enabled != 0;
+  m->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
+  return BQ_OK;
+}
+
+int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flops[BQ_PROFILE_KINDS],
+                            double bytes[BQ_PROFILE_KINDS], int64_t launches[BQ_PROFILE_KINDS]) {
+  if (!m || !ms || !flops || !bytes || !launches) return BQ_ERR_ARG;
+  for (int k = 0; k < BQ_PROFILE_KINDS; ++k) {
+    ms[k] = m->k_ms[k]; flops[k] = m->k_flops[k]; bytes[k] = m->k_bytes[k]; launches[k] = m->k_launches[k];
+  }
   return BQ_OK;
 }
 

@@ -1,0 +1,87 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, tiles sharded by WHOLE slides, and a single
+all-gather of the small per-slide aggregates.
+
+Why slide-aligned: the reference's slide means are row-order Kahan sums in the column dtype
+(pandas `group_mean`, reference threshold.py:191-192); summing per-GPU partials would change the
+rounding and can flip a threshold decision, so a slide is never split across ranks and every slide's
+reduction stays local and bit-exact.  The only exchange step is `all_gather_groups`: <= 40 B per slide
+over NCCL/NVLink (gloo in the CPU tests) -- latency-, not bandwidth-bound.
+
+`torch.distributed` is plumbing only; the arithmetic stays in libbiscuit_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GROUP_FIELDS = ("code", "count", "first_row", "y_pred", "uncertainty", "y_true_mean")
+
+
+def shard_bounds(tiles_per_slide, world_size: int):
+    """Contiguous, slide-aligned partition of a cohort balanced by tile count.
+
+    tiles_per_slide: tile counts in table order.  Returns [(slide_lo, slide_hi)] * world_size;
+    rank r owns slides [lo, hi) -- greedy prefix split at the slide boundary closest to r/world of
+    the tiles."""
+    counts = np.asarray(tiles_per_slide, dtype=np.int64)
+    n_slides = int(counts.shape[0])
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        j = int(np.searchsorted(cum, target, side="left"))
+        if j > 0 and abs(cum[j - 1] - target) <= abs(cum[min(j, n_slides)] - target):
+            j -= 1
+        j = min(max(j, cuts[-1]), n_slides)
+        cuts.append(j)
+    cuts.append(n_slides)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+def pack_groups(code_offset, counts, first_rows, row_offset, y_pred, uncertainty, y_true_mean):
+    """Local per-slide aggregates -> float64 [L, 6] message (float32 means are exact in float64)."""
+    L = len(counts)
+    msg = np.empty((L, len(GROUP_FIELDS)), dtype=np.float64)
+    msg[:, 0] = np.arange(L) + code_offset
+    msg[:, 1] = counts
+    msg[:, 2] = np.where(np.asarray(first_rows) >= 0, np.asarray(first_rows) + row_offset, -1)
+    msg[:, 3] = y_pred
+    msg[:, 4] = uncertainty
+    msg[:, 5] = y_true_mean
+    return msg
+
+
+def all_gather_groups(msg: np.ndarray, group=None, device=None):
+    """All-gather variable-length [L_r, 6] float64 blocks from every rank -> [sum L_r, 6] in rank
+    order (== table order, because shards are contiguous).  Works on NCCL (device tensors) and gloo."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return msg
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cpu") if backend == "gloo" else torch.device(device if device is not None else "cuda")
+    n_local = torch.tensor([msg.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = msg.shape[1]
+    pad = max(sizes) if sizes else 0
+    buf = torch.zeros((pad, width), dtype=torch.float64, device=dev)
+    if msg.shape[0]:
+        buf[: msg.shape[0]] = torch.from_numpy(np.ascontiguousarray(msg)).to(dev)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = [o[:s].cpu().numpy() for o, s in zip(out, sizes)]
+    return np.concatenate(parts, axis=0) if parts else msg
+
+
+def unpack_groups(msg: np.ndarray, dtype):
+    """-> dict of arrays for the surviving groups, ordered by first surviving row (first appearance)."""
+    alive = msg[:, 1] > 0
+    m = msg[alive]
+    order = np.argsort(m[:, 2], kind="stable")
+    m = m[order]
+    return {"code": m[:, 0].astype(np.int64), "count": m[:, 1].astype(np.int64),
+            "y_pred": m[:, 3].astype(dtype), "uncertainty": m[:, 4].astype(dtype),
+            "y_true": m[:, 5].astype(np.uint8)}

@@ -395,6 +395,80 @@ def apply(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
     return results, s_df
 
 
+def apply_sharded(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, keep="high_confidence",
+                  patients=None, level="slide", group=None):
+    """`apply` for a cohort sharded over ranks (one process per GPU, torch.distributed initialised).
+
+    Every rank passes ITS contiguous, slide-aligned shard of the tile table (see `dist.shard_bounds`;
+    a slide / patient must not straddle ranks).  Tile processing and the reference-order slide
+    reduction run locally on each GPU; the per-slide aggregates (<= 48 B per slide) are all-gathered
+    once and the group-level thresholding runs replicated, so every rank returns the same
+    (results, s_df) `apply` would return on the concatenated table."""
+    import torch.distributed as tdist
+    from . import dist as bdist
+    assert keep in ("high_confidence", "low_confidence")
+    assert not (level == "patient" and patients is None)
+    log.debug(f"Applying tile UQ threshold of {tile_uq:.5f}")
+    if patients:
+        df["patient"] = df["slide"].map(patients)
+    df[level]
+    _check_columns(df)
+    world = tdist.get_world_size(group) if tdist.is_available() and tdist.is_initialized() else 1
+    with _open_table(df) as tab:
+        _tile_stage(tab, df, tile_pred, patients)
+        codes, uniques = _factorize(df[level])
+        n_keys = len(uniques) + int((codes < 0).any())
+        tile_uq_eff = _cmp_scalar(tile_uq, tab.dtype) if tile_uq else None
+        tab.set_groups(codes, len(uniques))
+        tab.set_filter(tile_uq_eff)
+        gp, gu, gt, cnt, first = tab.group_reduce()
+        ctx, dtype = tab.ctx, tab.dtype
+    names = [str(u) for u in uniques]
+    if world > 1:
+        meta = [None] * world
+        tdist.all_gather_object(meta, (len(uniques), len(df), n_keys, names), group=group)
+        rank = tdist.get_rank(group)
+        code_off = sum(m[0] for m in meta[:rank])
+        row_off = sum(m[1] for m in meta[:rank])
+        n_before = sum(m[2] for m in meta)
+        all_names = [nm for m in meta for nm in m[3]]
+    else:
+        code_off, row_off, n_before, all_names = 0, 0, n_keys, names
+    msg = bdist.pack_groups(code_off, cnt, first, row_off, gp, gu, gt)
+    g = bdist.unpack_groups(bdist.all_gather_groups(msg, group=group, device=f"cuda:{ctx.device}"), dtype)
+    yp, u, yt = g["y_pred"], g["uncertainty"], g["y_true"]
+    if not len(yt):
+        log.error("Unable to process slide predictions")
+        return {k: None for k in _RESULT_KEYS}, None
+    base = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, _ffi.KEEP_ALL, 0.0)
+    s_df = pd.DataFrame({
+        level: pd.Series([all_names[c] for c in g["code"]]),
+        "error": pd.Series(base["error"]),
+        "uncertainty": pd.Series(u),
+        "correct": base["correct"].view(np.bool_),
+        "incorrect": pd.Series(base["incorrect"]).astype(int),
+        "y_true": pd.Series(yt),
+        "y_pred": pd.Series(yp),
+        "y_pred_bin": pd.Series(base["y_pred_bin"].view(np.bool_)).astype(int),
+    })
+    if slide_uq:
+        mode = _ffi.KEEP_HIGH if keep == "high_confidence" else _ffi.KEEP_LOW
+        uq_eff = _cmp_scalar(slide_uq, u.dtype)
+    else:
+        mode, uq_eff = _ffi.KEEP_ALL, 0.0
+    cols = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, mode, uq_eff)
+    if slide_uq:
+        s_df = s_df.loc[cols["include"].view(np.bool_)]
+    auc = _auc_included(ctx, yp, yt, cols["include"])
+    tp, fp, tn, fn = cols["confusion"]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        results = {"auc": auc, "percent_incl": len(s_df) / n_before,
+                   "acc": (tp + tn) / (tp + tn + fp + fn),
+                   "sensitivity": tp / (tp + fn),
+                   "specificity": tn / (tn + fp)}
+    return results, s_df
+
+
 def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pred="detect",
            plot=False, patients=None):
     """Detect optimal tile- and slide-level uncertainty thresholds (reference threshold.py:364-475).

@@ -140,8 +140,21 @@ class UncertaintyInterface:
         s = tuple(int(x) for x in shape)
         return out[: int(np.prod(s))].reshape(s).copy()
 
-    def set_profiling(self, on: bool):
-        _ffi.check(self.ctx.handle, self.lib.bq_model_set_profiling(self.h, int(on)), "bq_model_set_profiling")
+    KERNEL_FAMILIES = ("tile_stats", "conv1", "gemm_conv2", "gemm_pointwise", "depthwise", "maxpool_add",
+                       "subsample", "gap", "head_gemm", "mc_expand", "head_final")
+
+    def set_profiling(self, level: int):
+        """0 off, 1 per-stage CUDA-event times, 2 per-kernel-family times + algorithmic work"""
+        _ffi.check(self.ctx.handle, self.lib.bq_model_set_profiling(self.h, int(level)), "bq_model_set_profiling")
+
+    def kernel_profile(self):
+        """{family: {ms, flops, bytes, launches}} of the last predict() (profiling level 2)"""
+        n = 16
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        la = (C.c_int64 * n)()
+        _ffi.check(self.ctx.handle, self.lib.bq_model_kernel_profile(self.h, ms, fl, by, la), "bq_model_kernel_profile")
+        return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(la[i]))
+                for i, k in enumerate(self.KERNEL_FAMILIES)}
 
     def last_stage_ms(self):
         ms = (C.c_float * 8)()

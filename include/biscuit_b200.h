@@ -170,8 +170,19 @@ int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const cha
 
 /* per-stage device time of the last bq_predict_uq call, in ms: {stats+conv1, conv2, entry, middle,
  * exit, head} -- measured with CUDA events on the ctx stream when enabled */
-int bq_model_set_profiling(bq_model* m, int enabled);
+int bq_model_set_profiling(bq_model* m, int enabled);   /* 0 off, 1 per stage, 2 per kernel family */
 int bq_model_last_stage_ms(bq_model* m, float ms[8]);
+
+/* Per-kernel-family accounting of the last bq_predict_uq call (profiling level 2): summed CUDA-event time
+ * of every launch of the family on the ctx stream, the ALGORITHMIC flops / bytes those launches processed
+ * (DESIGN.md states the per-unit figures) and the launch count.  bench.py's `roofline` is built from this. */
+enum {
+  BQ_K_STATS = 0, BQ_K_CONV1 = 1, BQ_K_GEMM_CONV2 = 2, BQ_K_GEMM_PW = 3, BQ_K_DW = 4, BQ_K_POOLADD = 5,
+  BQ_K_SUBSAMPLE = 6, BQ_K_GAP = 7, BQ_K_HEAD_GEMM = 8, BQ_K_MC_EXPAND = 9, BQ_K_HEAD_FINAL = 10,
+  BQ_PROFILE_KINDS = 16
+};
+int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flops[BQ_PROFILE_KINDS],
+                            double bytes[BQ_PROFILE_KINDS], int64_t launches[BQ_PROFILE_KINDS]);
 
 #ifdef __cplusplus
 }
