@@ -157,33 +157,56 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_K>
+// TMA store: smem tile -> global (bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int kEpiCols = 64;                       // epilogue chunk: 128 rows x 64 bf16 columns = 16 KB
+constexpr int kEpiBytes = kBM * kEpiCols * 2;
+
+// TMA_EPI = true : output (and residual) tiles move through shared memory with TMA (coalesced 128-byte rows,
+//                  hardware clipping of the M / N tails); 3 operand stages.
+// TMA_EPI = false: each epilogue thread stores its own row directly (used by the implicit 3x3 convolution, whose
+//                  rows are compacted on the way out, 128 contiguous bytes per thread).
+template <int BLOCK_K, bool TMA_EPI>
 struct SmemPlan {
-  static constexpr int kStages = BLOCK_K == 64 ? 4 : 6;
+  static constexpr int kStages = TMA_EPI ? 3 : (BLOCK_K == 64 ? 4 : 6);
   static constexpr int kABytes = kBM * BLOCK_K * 2;
   static constexpr int kBBytes = kBNMax * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kOutOffset = kStages * kStageBytes;             // 2 x out staging, 2 x residual staging
+  static constexpr int kResOffset = kOutOffset + (TMA_EPI ? 2 * kEpiBytes : 0);
+  static constexpr int kBarOffset = kResOffset + (TMA_EPI ? 2 * kEpiBytes : 0);
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + tmem slot, + slack for 1024 B alignment
 };
 
-template <int BLOCK_K>
+template <int BLOCK_K, bool TMA_EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
-  using Plan = SmemPlan<BLOCK_K>;
+  using Plan = SmemPlan<BLOCK_K, TMA_EPI>;
   constexpr int STAGES = Plan::kStages;
   constexpr int SWZ = BLOCK_K * 2;     // bytes per smem row == swizzle span
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));      // generic pointer to the aligned base
   const uint32_t bar_base = smem_base + Plan::kBarOffset;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kAccStages + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages);
-  volatile uint32_t* tmem_slot_ptr =
-      (volatile uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 * kAccStages + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages + 2);
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kBM - 1) / kBM;
@@ -195,8 +218,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (TMA_EPI) { tma_prefetch_desc(&tmap_out); if (p.residual) tma_prefetch_desc(&tmap_res); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kAccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(res_bar(0), 1); mbar_init(res_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -263,40 +288,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
     const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
     int as = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
-      int n_cols = p.N - n0;
-      if (n_cols > p.bn_box) n_cols = p.bn_box;
-      const int m = m0 + quad * 32 + lane;
-      // output row (conv mode drops rows outside the valid window and compacts the rest)
-      long long orow = m;
-      bool row_ok = m < p.M;
-      if (p.conv_mode && row_ok) {
-        const int img = m / p.in_hw, rem = m - img * p.in_hw;
-        const int y = rem / p.in_w, x = rem - y * p.in_w;
-        row_ok = (y < p.out_h) && (x < p.out_w);
-        orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
+    if constexpr (TMA_EPI) {
+      const bool leader = (warp == 2 && lane == 0);
+      const bool has_res = p.residual != nullptr;
+      uint32_t cc = 0;                                   // running chunk counter: buffer = cc & 1
+      if (leader && has_res && (int)blockIdx.x < total_tiles) {
+        const int t0 = blockIdx.x;
+        mbar_expect_tx(res_bar(0), kEpiBytes);
+        tma_load_2d(smem_base + Plan::kResOffset, &tmap_res, res_bar(0), (t0 % n_tiles) * p.bn_box, (t0 / n_tiles) * kBM);
       }
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
-      for (int c = 0; c < n_cols; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (row_ok) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
+        int n_cols = p.N - n0;
+        if (n_cols > p.bn_box) n_cols = p.bn_box;
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
+        for (int c = 0; c < n_cols; c += kEpiCols, ++cc) {
+          const uint32_t buf = cc & 1u;
+          uint8_t* out_st = smem_gen + Plan::kOutOffset + buf * kEpiBytes;
+          const uint8_t* res_st = smem_gen + Plan::kResOffset + buf * kEpiBytes;
+          uint32_t v[64];
+          {
+            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+            tmem_ld_32x32b_x32(t_row + (uint32_t)c, v0);
+            tmem_ld_32x32b_x32(t_row + (uint32_t)c + 32u, v1);
+            tmem_ld_wait();
+          }
+          if (has_res) mbar_wait(res_bar(buf), (cc >> 1) & 1u);
           const int n = n0 + c;
-          __nv_bfloat16* optr = p.out + orow * p.ldc + n;
-          const __nv_bfloat16* rptr = p.residual ? p.residual + orow * p.ldr + n : nullptr;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 8; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
             if (n + g * 8 < p.N) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              // separately rounded multiply and add (no FMA contraction): same rounding sequence as the
-              // oracle's `acc * scale + shift`
               if (p.scale) {
                 const float4 s0 = __ldg((const float4*)(p.scale + n + g * 8));
                 const float4 s1 = __ldg((const float4*)(p.scale + n + g * 8 + 4));
@@ -314,32 +343,133 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], sh[j]);
               }
-              if (rptr) {
-                const uint4 r = *(const uint4*)(rptr + g * 8);
-                const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 rf = __bfloat1622float2(rb[j]);
-                  f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
-                }
+              for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            }
+            const uint32_t sw_off = (uint32_t)row_in_tile * 128u + (uint32_t)((g ^ (row_in_tile & 7)) << 4);
+            if (has_res) {
+              const uint4 r = *(const uint4*)(res_st + sw_off);
+              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 rf = __bfloat1622float2(rb[j]);
+                f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
               }
-              if (p.relu) {
+            }
+            if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            uint4 o;
+            __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *(uint4*)(out_st + sw_off) = o;
+          }
+          fence_async_smem();                       // generic-proxy smem writes -> visible to the TMA engine
+          if (leader) tma_store_wait_read0();       // the previous chunk's store has finished reading its buffer
+          epi_barrier();
+          if (leader) {
+            tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n, m0);
+            tma_store_commit();
+            if (has_res) {
+              // prefetch the residual chunk of the NEXT epilogue step into the other buffer (its last readers
+              // finished before the barrier above)
+              int nt = tile, nc = c + kEpiCols;
+              if (nc >= n_cols) { nt = tile + gridDim.x; nc = 0; }
+              if (nt < total_tiles) {
+                mbar_expect_tx(res_bar(buf ^ 1u), kEpiBytes);
+                tma_load_2d(smem_base + Plan::kResOffset + (buf ^ 1u) * kEpiBytes, &tmap_res, res_bar(buf ^ 1u),
+                            (nt % n_tiles) * p.bn_box + nc, (nt / n_tiles) * kBM);
               }
-              uint4 o;
-              __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *(uint4*)(optr + g * 8) = o;
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == kAccStages) { as = 0; aph ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (++as == kAccStages) { as = 0; aph ^= 1u; }
+      if (leader) tma_store_wait_all();
+    } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
+        int n_cols = p.N - n0;
+        if (n_cols > p.bn_box) n_cols = p.bn_box;
+        const int m = m0 + row_in_tile;
+        // output row (conv mode drops rows outside the valid window and compacts the rest)
+        long long orow = m;
+        bool row_ok = m < p.M;
+        if (p.conv_mode && row_ok) {
+          const int img = m / p.in_hw, rem = m - img * p.in_hw;
+          const int y = rem / p.in_w, x = rem - y * p.in_w;
+          row_ok = (y < p.out_h) && (x < p.out_w);
+          orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
+        }
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
+        for (int c = 0; c < n_cols; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n = n0 + c;
+            __nv_bfloat16* optr = p.out + orow * p.ldc + n;
+            const __nv_bfloat16* rptr = p.residual ? p.residual + orow * p.ldr + n : nullptr;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n + g * 8 < p.N) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                // separately rounded multiply and add (no FMA contraction): same rounding sequence as the
+                // oracle's `acc * scale + shift`
+                if (p.scale) {
+                  const float4 s0 = __ldg((const float4*)(p.scale + n + g * 8));
+                  const float4 s1 = __ldg((const float4*)(p.scale + n + g * 8 + 4));
+                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], sc[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], p.alpha);
+                }
+                if (p.shift) {
+                  const float4 h0 = __ldg((const float4*)(p.shift + n + g * 8));
+                  const float4 h1 = __ldg((const float4*)(p.shift + n + g * 8 + 4));
+                  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], sh[j]);
+                }
+                if (rptr) {
+                  const uint4 r = *(const uint4*)(rptr + g * 8);
+                  const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 rf = __bfloat1622float2(rb[j]);
+                    f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                uint4 o;
+                __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                *(uint4*)(optr + g * 8) = o;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == kAccStages) { as = 0; aph ^= 1u; }
+      }
     }
   }
   tc_fence_before();
@@ -347,6 +477,285 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x N tile with ONE tcgen05.mma stream.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (N/2 rows), so operand traffic from L2 per
+// CTA per k-block drops from 48 KB to 32 KB (the 1-CTA kernel is L2->SM bound: ncu shows 25 % tensor-pipe
+// activity with neither L2 nor HBM saturated).  Protocol (after DeepGEMM's sm100 kernels):
+//   full[s]   lives in the LEADER (cluster rank 0): 2 arrivals (leader expect_tx for both CTAs' bytes, peer
+//             remote arrive); both CTAs' TMA loads complete_tx on the leader's barrier (.cta_group::2 form)
+//   empty[s], tmem_full[a]  live in BOTH CTAs, signalled by multicast tcgen05.commit (mask 0b11)
+//   tmem_empty[a] lives in the leader: 8 arrivals (4 epilogue warps x 2 CTAs, remote via mapa)
+// Only the leader's warp 1 issues MMAs; each CTA runs its own TMA producer and its own epilogue on its
+// 128 accumulator rows.
+// =====================================================================================================
+constexpr int k2Stages = 4;
+constexpr int k2EpiWarps = 8;                        // two warps per TMEM lane quadrant (32 columns of a chunk each)
+constexpr int k2Threads = 64 + 32 * k2EpiWarps;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
+constexpr int k2MaxN = 2048;                         // per-channel scale/shift staged in smem for the whole N
+struct SmemPlan2 {
+  static constexpr int kABytes = kBM * 64 * 2;                 // 16 KB
+  static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (half of the N tile)
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutOffset = k2Stages * kStageBytes;
+  static constexpr int kResOffset = kOutOffset + 2 * kEpiBytes;
+  static constexpr int kScaleOffset = kResOffset + 2 * kEpiBytes;      // float scale[k2MaxN], shift[k2MaxN]
+  static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"((uint64_t)tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                         const GemmParams p) {
+  using Plan = SmemPlan2;
+  constexpr int STAGES = k2Stages;
+  constexpr int BLOCK_K = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Plan::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kAccStages + a); };
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 * kAccStages + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages + 2);
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * kBM - 1) / (2 * kBM);              // 256-row pair tiles
+  const int n_tiles = (p.N + p.bn_box - 1) / p.bn_box;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t b_box_bytes = (uint32_t)(p.bn_box / 2) * BLOCK_K * 2;
+  const uint32_t stage_tx = 2u * (Plan::kABytes + b_box_bytes);     // both CTAs' bytes land on the leader's barrier
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (p.residual) tma_prefetch_desc(&tmap_res);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < kAccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * k2EpiWarps); }
+    mbar_init(res_bar(0), 1); mbar_init(res_bar(1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // per-channel epilogue constants -> smem (read back as broadcast LDS; global loads here stalled the epilogue)
+  float* s_scale = (float*)(smem_gen + Plan::kScaleOffset);
+  float* s_shift = s_scale + k2MaxN;
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    s_scale[i] = p.scale ? __ldg(p.scale + i) : p.alpha;
+    s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.f;
+  }
+  cluster_sync_all();                        // both CTAs resident before the paired TMEM allocation
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                        // barriers initialised + TMEM allocated in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA: its A rows + its half of B) =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m0 = (tile / n_tiles) * (2 * kBM) + (int)rank * kBM;
+        const int n0 = (tile % n_tiles) * p.bn_box;
+        int n_cols = p.N - n0;
+        if (n_cols > p.bn_box) n_cols = p.bn_box;
+        n_cols = (n_cols + 15) & ~15;
+        const int nb0 = n0 + (int)rank * (n_cols / 2);            // this CTA's half of the N tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (is_leader) mbar_expect_tx(full_bar(s), stage_tx);
+          else mbar_arrive_remote(full_bar(s), 0);
+          const uint32_t a_dst = smem_base + s * Plan::kStageBytes, b_dst = a_dst + Plan::kABytes;
+          tma_load_2d_2cta(a_dst, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
+          tma_load_2d_2cta(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, nb0);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA, one thread =====================
+    if (is_leader && lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int n0 = (tile % n_tiles) * p.bn_box;
+        int n_cols = p.N - n0;
+        if (n_cols > p.bn_box) n_cols = p.bn_box;
+        n_cols = (n_cols + 15) & ~15;
+        const uint32_t idesc = make_idesc(2 * kBM, n_cols);
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + s * Plan::kStageBytes, b_src = a_src + Plan::kABytes;
+          int ksteps = BLOCK_K / 16;
+          if (kb == num_kb - 1) ksteps = (p.K - kb * BLOCK_K + 15) / 16;
+          const uint64_t da = make_smem_desc<128>(a_src), db = make_smem_desc<128>(b_src);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2cta(empty_bar(s));
+          if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(as));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++as == kAccStages) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: each CTA drains its own 128 accumulator rows =====================
+    // 8 warps: warp -> (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4); a chunk is 128 rows x 64 cols.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    int as = 0; uint32_t aph = 0;
+    const bool leader = (warp == 2 && lane == 0);
+    const bool has_res = p.residual != nullptr;
+    uint32_t cc = 0;
+    if (leader && has_res && cluster_id < total_tiles) {
+      mbar_expect_tx(res_bar(0), kEpiBytes);
+      tma_load_2d(smem_base + Plan::kResOffset, &tmap_res, res_bar(0), (cluster_id % n_tiles) * p.bn_box,
+                  (cluster_id / n_tiles) * (2 * kBM) + (int)rank * kBM);
+    }
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m0 = (tile / n_tiles) * (2 * kBM) + (int)rank * kBM, n0 = (tile % n_tiles) * p.bn_box;
+      int n_cols = p.N - n0;
+      if (n_cols > p.bn_box) n_cols = p.bn_box;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
+      for (int c = 0; c < n_cols; c += kEpiCols, ++cc) {
+        const uint32_t buf = cc & 1u;
+        uint8_t* out_st = smem_gen + Plan::kOutOffset + buf * kEpiBytes;
+        const uint8_t* res_st = smem_gen + Plan::kResOffset + buf * kEpiBytes;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(c + half * 32), v);
+        tmem_ld_wait();
+        if (has_res) mbar_wait(res_bar(buf), (cc >> 1) & 1u);
+        const int n = n0 + c + half * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+          const int ng = n + g * 8;
+          if (ng < p.N) {
+            const float4 s0 = *(const float4*)(s_scale + ng), s1 = *(const float4*)(s_scale + ng + 4);
+            const float4 h0 = *(const float4*)(s_shift + ng), h1 = *(const float4*)(s_shift + ng + 4);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          }
+          const int chunk16 = half * 4 + g;                // 16-byte column group inside the 128-byte smem row
+          const uint32_t sw_off = (uint32_t)row_in_tile * 128u + (uint32_t)((chunk16 ^ (row_in_tile & 7)) << 4);
+          if (has_res) {
+            const uint4 r = *(const uint4*)(res_st + sw_off);
+            const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __bfloat1622float2(rb[j]);
+              f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          uint4 o;
+          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *(uint4*)(out_st + sw_off) = o;
+        }
+        fence_async_smem();
+        if (leader) tma_store_wait_read0();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (leader) {
+          tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n0 + c, m0);
+          tma_store_commit();
+          if (has_res) {
+            int nt = tile, nc = c + kEpiCols;
+            if (nc >= n_cols) { nt = tile + num_clusters; nc = 0; }
+            if (nt < total_tiles) {
+              mbar_expect_tx(res_bar(buf ^ 1u), kEpiBytes);
+              tma_load_2d(smem_base + Plan::kResOffset + (buf ^ 1u) * kEpiBytes, &tmap_res, res_bar(buf ^ 1u),
+                          (nt % n_tiles) * p.bn_box + nc, (nt / n_tiles) * (2 * kBM) + (int)rank * kBM);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(as), 0);     // accumulator stage drained -> leader's barrier
+      if (++as == kAccStages) { as = 0; aph ^= 1u; }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();        // no CTA may exit (or free TMEM) while its partner can still signal / read it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 

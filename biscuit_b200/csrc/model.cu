@@ -182,7 +182,8 @@ struct Op {
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
   int blk_k = 64;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tr; // A, B, output, residual
+  CUtensorMap tb2;            // B with a half-height box (2-CTA kernel: each CTA stages N/2 rows)
 };
 
 struct Arena {                // activation scratch: a handful of max-size buffers
@@ -197,6 +198,9 @@ struct bq_model {
   bq_model_config cfg{};
   bool weights_loaded = false;
   bool use_simt = false;
+  bool dw_v1 = false;
+  bool gemm_direct_epi = false;
+  bool gemm_2cta = true;
   int max_batch = 0;
   int px = 299;
 
@@ -221,7 +225,7 @@ struct bq_model {
 
   std::vector<Op> plan;
   // head GEMM descriptors are rebuilt when T changes
-  struct HeadGemm { GemmParams gp; CUtensorMap ta, tb; };
+  struct HeadGemm { GemmParams gp; CUtensorMap ta, tb, tc, tb2; };
   std::vector<HeadGemm> head_gemms;
   int head_T = -1;
 
@@ -270,7 +274,8 @@ void kprofile_collect(bq_model* m) {
   m->krec.clear();
 }
 
-int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, int blk_k) {
+int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                const CUtensorMap& tr, int blk_k, const CUtensorMap* tb_half = nullptr) {
   bq_ctx* ctx = m->ctx;
   if (gp.M <= 0) return BQ_OK;
   if (m->use_simt) {
@@ -279,14 +284,21 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
     BQ_LAUNCH_CHECK(ctx);
     return BQ_OK;
   }
-  const int m_tiles = (gp.M + bq::sm100::kBM - 1) / bq::sm100::kBM;
+  using namespace bq::sm100;
+  const int m_tiles = (gp.M + kBM - 1) / kBM;
   const int n_tiles = (gp.N + gp.bn_box - 1) / gp.bn_box;
   int grid = m_tiles * n_tiles;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
-  if (blk_k == 64) {
-    bq::sm100::gemm_tcgen05_kernel<64><<<grid, bq::sm100::kThreads, bq::sm100::SmemPlan<64>::kTotal, ctx->stream>>>(ta, tb, gp);
+  if (blk_k == 32) {
+    gemm_tcgen05_kernel<32, false><<<grid, kThreads, SmemPlan<32, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
+  } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
+    const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
+    int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
+    gemm_tcgen05_2cta_kernel<<<2 * clusters, k2Threads, SmemPlan2::kTotal, ctx->stream>>>(ta, *tb_half, tc, tr, gp);
+  } else if (m->gemm_direct_epi) {
+    gemm_tcgen05_kernel<64, false><<<grid, kThreads, SmemPlan<64, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else {
-    bq::sm100::gemm_tcgen05_kernel<32><<<grid, bq::sm100::kThreads, bq::sm100::SmemPlan<32>::kTotal, ctx->stream>>>(ta, tb, gp);
+    gemm_tcgen05_kernel<64, true><<<grid, kThreads, SmemPlan<64, true>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   }
   BQ_LAUNCH_CHECK(ctx);
   return BQ_OK;
@@ -322,6 +334,10 @@ int make_gemm(bq_model* m, Op& op, const bf16* a, int rows_per_tile, const PwWei
   int rc;
   if ((rc = make_tmap(m->ctx, &op.ta, a, (uint64_t)g.M, (uint64_t)w.ktot, (uint64_t)w.ktot, 128, 64))) return rc;
   if ((rc = make_tmap(m->ctx, &op.tb, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, g.bn_box, 64))) return rc;
+  if ((rc = make_tmap(m->ctx, &op.tc, out, (uint64_t)g.M, (uint64_t)w.cout, (uint64_t)w.cout, 128, 64))) return rc;
+  op.tr = op.tc;
+  if (residual && (rc = make_tmap(m->ctx, &op.tr, residual, (uint64_t)g.M, (uint64_t)w.cout, (uint64_t)w.cout, 128, 64))) return rc;
+  if ((rc = make_tmap(m->ctx, &op.tb2, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, g.bn_box / 2, 64))) return rc;
   return BQ_OK;
 }
 
@@ -366,6 +382,7 @@ int build_plan(bq_model* m) {
     g.b_ptr = (const bf16*)m->conv2.w.p; g.ldb = 288;
     if ((rc = make_tmap(ctx, &op.ta, A.p(0), (uint64_t)s1 * s1 * B, 32, 32, 128, 32))) return rc;
     if ((rc = make_tmap(ctx, &op.tb, m->conv2.w.p, 64, 288, 288, 64, 32))) return rc;
+    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb;      // unused by the direct-store epilogue
     op.Ho = s2; op.Wo = s2; op.Cout = 64;
     m->plan.push_back(op);
   }
@@ -469,12 +486,22 @@ int run_op(bq_model* m, Op& op, int nb) {
       const double kin = g.conv_mode ? g.K / 9 : g.K;
       KScope ks(m, g.conv_mode ? BQ_K_GEMM_CONV2 : BQ_K_GEMM_PW, 2.0 * rows_out * g.N * g.K,
                 act * ((double)g.M * kin + rows_out * g.N * (g.residual ? 2 : 1) + (double)g.N * g.K));
-      return launch_gemm(m, g, op.ta, op.tb, op.blk_k);
+      return launch_gemm(m, g, op.ta, op.tb, op.tc, op.tr, op.blk_k, g.conv_mode ? nullptr : &op.tb2);
     }
     case OP_DW: {
       KScope ks(m, BQ_K_DW, 2.0 * 9 * nb * op.H * op.W * op.C, 2 * act * nb * op.H * op.W * op.C);
-      bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
-          op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
+      if (m->dw_v1) {
+        bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
+            op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
+      } else {
+        const int CC = (op.C % 64 == 0) ? 64 : 56;              // 728 = 13 x 56
+        const int tiles = (op.H + bq::kDwTile - 1) / bq::kDwTile;
+        dim3 grid((op.C + CC - 1) / CC, tiles * tiles, nb);
+        const int threads = (CC / 4) * bq::kDwTile;
+        const size_t smem = (size_t)bq::kDwHalo * bq::kDwHalo * CC * sizeof(bf16);
+        bq::depthwise3x3_smem_kernel<<<grid, threads, smem, ctx->stream>>>(op.in, op.dw, op.out, op.H, op.W, op.C, CC,
+                                                                        tiles, tiles, op.relu_in);
+      }
       break;
     }
     case OP_POOLADD: {
@@ -552,6 +579,8 @@ int prepare_head(bq_model* m, int T) {
     m->head_gemms[i].gp = op.gp;
     m->head_gemms[i].ta = op.ta;
     m->head_gemms[i].tb = op.tb;
+    m->head_gemms[i].tc = op.tc;
+    m->head_gemms[i].tb2 = op.tb2;
   }
   m->head_T = T;
   return BQ_OK;
@@ -587,7 +616,7 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
       g.M = nb * T;
     }
     KScope ks(m, BQ_K_HEAD_GEMM, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
-    if ((rc = launch_gemm(m, g, hg.ta, hg.tb, 64))) return rc;
+    if ((rc = launch_gemm(m, g, hg.ta, hg.tb, hg.tc, hg.tc, 64, &hg.tb2))) return rc;
   }
   const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
   const int Teff = Hn == 1 ? 1 : T;
@@ -630,11 +659,21 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->px = cfg->tile_px;
   const char* g = getenv("BQ_GEMM");
   m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
+  m->gemm_direct_epi = g && strcmp(g, "direct") == 0;   // debug switch: per-thread global stores in the epilogue
+  m->gemm_2cta = !(g && (strcmp(g, "1cta") == 0 || strcmp(g, "direct") == 0));   // default: cta_group::2 pairs
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan2::kTotal);
+  const char* dwv = getenv("BQ_DW");
+  m->dw_v1 = dwv && strcmp(dwv, "v1") == 0;    // debug switch: first-generation depthwise kernel
+  cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::kDwHalo * bq::kDwHalo * 64 * (int)sizeof(bf16));
   for (auto& e : m->ev) cudaEventCreate(&e);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan<64>::kTotal);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan<32>::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan<64, true>::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan<64, false>::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan<32, false>::kTotal);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete m; return bq_fail(ctx, BQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   *out = m;
