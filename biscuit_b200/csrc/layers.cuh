@@ -8,6 +8,7 @@
 //   head        -- Philox4x32-10 dropout masks, masked operand expansion, logits + softmax + mean/std over T
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -219,52 +220,33 @@ __device__ __forceinline__ void dw_load3(const bf16* row, int CC, float (&d)[3][
   }
 }
 __global__ void __launch_bounds__(320)
-depthwise3x3_smem_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][C]*/, bf16* __restrict__ out,
-                         int H, int W, int C, int CC /*channels per block: 64 or 56*/, int tiles_x, int tiles_y,
-                         int relu_in) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
+depthwise3x3_smem_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W, H, N], box [CC, 21, 21, 1]*/,
+                         const float* __restrict__ w /*[9][C]*/, bf16* __restrict__ out, int H, int W, int C,
+                         int CC /*channels per block: 64 or 56*/, int tiles_x, int relu_in) {
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  __shared__ __align__(8) uint64_t fill_bar;
   bf16* tile = (bf16*)dw_smem;                       // [kDwHalo][kDwHalo][CC]
   const int cpc = CC >> 2;                           // 4-channel groups per pixel
   const int c0 = blockIdx.x * CC;
-  const int cvalid = min(CC, C - c0);                // last chunk may be partial (multiple of 8)
   const int ty0 = (blockIdx.y / tiles_x) * kDwTile, tx0 = (blockIdx.y % tiles_x) * kDwTile;
   const int img = blockIdx.z;
-  const bf16* src = in + (int64_t)img * H * W * C + c0;
-  // ---- fill: 16-byte chunks, zero outside the image, 4 loads in flight per thread
-  const int vec_per_px = cvalid >> 3;
-  const int total_vec = kDwHalo * kDwHalo * vec_per_px;
-  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
-  for (int i0 = threadIdx.x; i0 < total_vec; i0 += blockDim.x * 4) {
-    uint4 val[4];
-    int pos[4], vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      val[u] = make_uint4(0u, 0u, 0u, 0u);
-      pos[u] = -1;
-      if (i < total_vec) {
-        vv[u] = i % vec_per_px;
-        pos[u] = i / vec_per_px;
-        const int hy = pos[u] / kDwHalo, hx = pos[u] - hy * kDwHalo;
-        const int y = ty0 + hy - 1, x = tx0 + hx - 1;
-        if (y >= 0 && y < H && x >= 0 && x < W)
-          val[u] = __ldg((const uint4*)(src + ((int64_t)y * W + x) * C + vv[u] * 8));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (pos[u] < 0) continue;
-      if (relu_in) {
-        __nv_bfloat162* b = (__nv_bfloat162*)&val[u];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = __hmax2(b[j], z2);
-      }
-      *(uint4*)(tile + (size_t)pos[u] * CC + vv[u] * 8) = val[u];
-    }
+  // ---- fill: ONE TMA tile load per block; the halo outside the image is zero-filled by the TMA unit
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&fill_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"((uint32_t)(kDwHalo * kDwHalo * CC * 2))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(tile)), "l"((uint64_t)&tmap_in), "r"(bar), "r"(c0), "r"(tx0 - 1),
+          "r"(ty0 - 1), "r"(img)
+        : "memory");
   }
   const int c4 = threadIdx.x % cpc, px = threadIdx.x / cpc;      // blockDim = cpc * kDwTile
   const int th = min(kDwTile, H - ty0), tw = min(kDwTile, W - tx0);
-  const bool active = (c4 * 4 < cvalid) && (px < tw);
+  const bool active = px < tw;
   float wr[9][4];
   if (active) {
 #pragma unroll
@@ -273,7 +255,31 @@ depthwise3x3_smem_kernel(const bf16* __restrict__ in, const float* __restrict__ 
       wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
     }
   }
-  __syncthreads();
+  __syncthreads();                                               // barrier initialised before anyone polls it
+  {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  if (relu_in) {                                                 // ReLU once per element, in place
+    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+    const int total_vec = kDwHalo * kDwHalo * CC / 8;
+    for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
+      uint4 v = *(uint4*)(tile + (size_t)i * 8);
+      __nv_bfloat162* b = (__nv_bfloat162*)&v;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = __hmax2(b[j], z2);
+      *(uint4*)(tile + (size_t)i * 8) = v;
+    }
+    __syncthreads();
+  }
   if (!active) return;
   const bf16* col = tile + (size_t)px * CC + c4 * 4;             // halo column px (= image column px - 1)
   const size_t row_stride = (size_t)kDwHalo * CC;

@@ -64,6 +64,22 @@ int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uin
   return BQ_OK;
 }
 
+// 4-D NHWC bf16 activation [N, H, W, C] with a [1, box_h, box_w, box_c] box, no swizzle (depthwise halo tiles)
+int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {c * sizeof(bf16), w * c * sizeof(bf16), h * w * c * sizeof(bf16)};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
+  return BQ_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights
 // ------------------------------------------------------------------------------------------------
@@ -389,9 +405,13 @@ int build_plan(bq_model* m) {
   X = 1;
   int H = s2, C = 64;
 
+  int dw_rc = BQ_OK;
   auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
     Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
     op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
+    const int CC = (c % 64 == 0) ? 64 : 56;
+    int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::kDwHalo, bq::kDwHalo, CC);
+    if (r && !dw_rc) dw_rc = r;
     m->plan.push_back(op);
   };
   auto add_gemm = [&](const bf16* a, int rows, const PwWeights& w, bf16* out, int relu, const bf16* resid, int stage,
@@ -450,7 +470,7 @@ int build_plan(bq_model* m) {
     if ((rc = add_gemm(A.p(t[0]), H * H, w2.pw, A.p(t[2]), 1, nullptr, 4, "block14", H, kFeatures))) return rc;
     Op op; op.kind = OP_GAP; op.stage = 4; op.in = A.p(t[2]); op.H = H; op.W = H; op.C = kFeatures; m->plan.push_back(op);
   }
-  return BQ_OK;
+  return dw_rc;
 }
 
 int run_op(bq_model* m, Op& op, int nb) {
@@ -499,8 +519,8 @@ int run_op(bq_model* m, Op& op, int nb) {
         dim3 grid((op.C + CC - 1) / CC, tiles * tiles, nb);
         const int threads = (CC / 4) * bq::kDwTile;
         const size_t smem = (size_t)bq::kDwHalo * bq::kDwHalo * CC * sizeof(bf16);
-        bq::depthwise3x3_smem_kernel<<<grid, threads, smem, ctx->stream>>>(op.in, op.dw, op.out, op.H, op.W, op.C, CC,
-                                                                        tiles, tiles, op.relu_in);
+        bq::depthwise3x3_smem_kernel<<<grid, threads, smem, ctx->stream>>>(op.ta, op.dw, op.out, op.H, op.W, op.C, CC,
+                                                                        tiles, op.relu_in);
       }
       break;
     }
