@@ -229,7 +229,11 @@ struct bq_model {
   DevBuf w3, b3;                               // fp32 [width][classes], [classes]
 
   // buffers
-  DevBuf tiles_dev;                            // uint8 staging [max_batch, px, px, 3]
+  DevBuf tiles_dev;                            // uint8 staging [max_batch, px, px, 3] (double-buffered with tiles_dev2)
+  DevBuf tiles_dev2;
+  const uint8_t* tiles_src = nullptr;          // where stats / conv1 read the current micro-batch from
+  cudaStream_t copy_stream = nullptr;          // H2D of micro-batch i+1 overlaps the backbone of micro-batch i
+  cudaEvent_t copied[2] = {}, consumed[2] = {};
   DevBuf mean, inv_std;                        // fp32 [max_batch]
   Arena arena;
   DevBuf feat, feat_bf16;                      // [max_batch, 2048]
@@ -371,7 +375,8 @@ int build_plan(bq_model* m) {
     BQ_CUDA(ctx, cudaMemset(b.p, 0, max_elems * sizeof(bf16) + 1024));
   }
   int rc;
-  if ((rc = bq_alloc(ctx, m->tiles_dev, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
+  if ((rc = bq_alloc(ctx, m->tiles_dev, (size_t)B * px * px * 3 + 64)) ||
+      (rc = bq_alloc(ctx, m->tiles_dev2, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
       (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
       (rc = bq_alloc(ctx, m->feat_bf16, (size_t)B * kFeatures * 2)) ||
       (rc = bq_alloc(ctx, m->out_mean, (size_t)B * m->cfg.n_classes * 4)) ||
@@ -485,14 +490,14 @@ int run_op(bq_model* m, Op& op, int nb) {
   switch (op.kind) {
     case OP_STATS: {
       KScope ks(m, BQ_K_STATS, 0, (double)nb * px * px * 3);
-      bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (int64_t)px * px * 3,
+      bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>(m->tiles_src, (int64_t)px * px * 3,
                                                         (float*)m->mean.p, (float*)m->inv_std.p);
       break;
     }
     case OP_CONV1: {
       KScope ks(m, BQ_K_CONV1, 2.0 * nb * op.Ho * op.Ho * 27 * 32, (double)nb * px * px * 3 + act * nb * op.Ho * op.Ho * 32);
       dim3 grid((op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, (op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, nb);
-      bq::conv1_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)m->tiles_dev.p, (const float*)m->mean.p,
+      bq::conv1_kernel<<<grid, 256, 0, ctx->stream>>>(m->tiles_src, (const float*)m->mean.p,
                                                      (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
                                                      (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
                                                      op.out, px, op.Ho);
@@ -551,6 +556,7 @@ int stage_tiles(bq_model* m, const uint8_t* tiles, int nb) {
   bq_ctx* ctx = m->ctx;
   const size_t bytes = (size_t)nb * m->px * m->px * 3;
   BQ_CUDA(ctx, cudaMemcpyAsync(m->tiles_dev.p, tiles, bytes, cudaMemcpyDefault, ctx->stream));
+  m->tiles_src = (const uint8_t*)m->tiles_dev.p;
   return BQ_OK;
 }
 
@@ -688,6 +694,11 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::kDwHalo * bq::kDwHalo * 64 * (int)sizeof(bf16));
   for (auto& e : m->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming);
+  }
   cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::sm100::SmemPlan<64, true>::kTotal);
   cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -706,6 +717,8 @@ void bq_model_destroy(bq_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   for (auto& e : m->kev) cudaEventDestroy(e);
+  if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
+  for (int i = 0; i < 2; ++i) { if (m->copied[i]) cudaEventDestroy(m->copied[i]); if (m->consumed[i]) cudaEventDestroy(m->consumed[i]); }
   delete m;
 }
 
@@ -804,10 +817,34 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
   if (m->profiling) for (auto& s : m->stage_ms) s = 0.f;
   if (m->profiling == 2)
     for (int k = 0; k < BQ_PROFILE_KINDS; ++k) { m->k_ms[k] = m->k_flops[k] = m->k_bytes[k] = 0; m->k_launches[k] = 0; }
-  for (int64_t i0 = 0; i0 < n; i0 += B) {
+  // Host tiles: double-buffered staging, the H2D copy of micro-batch i+1 runs on its own stream while the
+  // backbone of micro-batch i computes.  Device tiles are read in place.
+  const bool tiles_on_dev = bq_is_device_ptr(tiles);
+  uint8_t* stage[2] = {(uint8_t*)m->tiles_dev.p, (uint8_t*)m->tiles_dev2.p};
+  auto issue_copy = [&](int64_t i0c, int slot) -> int {
+    const int nbc = (int)((n - i0c < B) ? (n - i0c) : B);
+    BQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->consumed[slot], 0));   // previous reader of this slot done
+    BQ_CUDA(ctx, cudaMemcpyAsync(stage[slot], tiles + (size_t)i0c * tile_bytes, (size_t)nbc * tile_bytes,
+                                 cudaMemcpyHostToDevice, m->copy_stream));
+    BQ_CUDA(ctx, cudaEventRecord(m->copied[slot], m->copy_stream));
+    return BQ_OK;
+  };
+  if (!tiles_on_dev && n > 0) {
+    int rc0 = issue_copy(0, 0);
+    if (rc0) return rc0;
+  }
+  int64_t batch_idx = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += B, ++batch_idx) {
     const int nb = (int)((n - i0 < B) ? (n - i0) : B);
     int rc;
-    if ((rc = stage_tiles(m, tiles + (size_t)i0 * tile_bytes, nb))) return rc;
+    const int slot = (int)(batch_idx & 1);
+    if (tiles_on_dev) {
+      m->tiles_src = tiles + (size_t)i0 * tile_bytes;
+    } else {
+      if (i0 + B < n && (rc = issue_copy(i0 + B, slot ^ 1))) return rc;
+      BQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copied[slot], 0));
+      m->tiles_src = stage[slot];
+    }
     const uint8_t* mdev = nullptr;
     if (masks) {
       if (masks_on_dev) mdev = masks + (size_t)i0 * mask_per_tile;
@@ -818,6 +855,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
       }
     }
     if ((rc = run_backbone(m, nb, nullptr, nullptr))) return rc;
+    if (!tiles_on_dev) BQ_CUDA(ctx, cudaEventRecord(m->consumed[slot], ctx->stream));
     if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0, mdev))) return rc;
     if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
     if ((rc = bq_from_device(ctx, mean + (size_t)i0 * NC, m->out_mean.p, (size_t)nb * NC * 4)) ||

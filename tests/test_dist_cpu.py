@@ -1,0 +1,93 @@
+"""CPU tier (gloo, world_size 2): the multi-GPU host logic of the path -- slide-aligned sharding and the single
+all-gather of per-slide aggregates -- reproduces the single-process group table exactly.  The per-shard
+aggregates are produced here by the oracle's pandas-order Kahan mean (the CUDA reduction is checked against
+the same oracle in the GPU tier)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from biscuit_b200 import dist as bdist
+from oracle import synth, threshold_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _local_groups(df):
+    codes, uniques = df["slide"].factorize()
+    L = len(uniques)
+    gp, cnt = O.kahan_group_mean(df["y_pred"].to_numpy(), codes, L)
+    gu, _ = O.kahan_group_mean(df["uncertainty"].to_numpy(), codes, L)
+    gt, _ = O.kahan_group_mean(df["y_true"].to_numpy().astype(np.float64), codes, L)
+    first = np.array([np.flatnonzero(codes == g)[0] for g in range(L)], dtype=np.int64)
+    return list(uniques), gp, gu, gt, cnt, first
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        df = synth.tile_table(n_slides=11, tiles_per_slide=40, seed=21, ragged=True)
+        counts = df.groupby("slide", sort=False).size().to_numpy()
+        bounds = bdist.shard_bounds(counts, world)
+        lo, hi = bounds[rank]
+        row_lo, row_hi = int(counts[:lo].sum()), int(counts[:hi].sum())
+        local = df.iloc[row_lo:row_hi].reset_index(drop=True)
+        names, gp, gu, gt, cnt, first = _local_groups(local)
+        meta = [None] * world
+        dist.all_gather_object(meta, (len(names), len(local)))
+        code_off = sum(m[0] for m in meta[:rank])
+        row_off = sum(m[1] for m in meta[:rank])
+        msg = bdist.pack_groups(code_off, cnt, first, row_off, gp, gu, gt)
+        allmsg = bdist.all_gather_groups(msg)
+        g = bdist.unpack_groups(allmsg, np.float32)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **g, row_off=row_off, code_off=code_off)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        for _ in range(20):
+            counts = rng.integers(1, 3000, rng.integers(world, 60))
+            b = bdist.shard_bounds(counts, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == len(counts)
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))       # contiguous, slide aligned
+            assert all(lo <= hi for lo, hi in b)
+            loads = [counts[lo:hi].sum() for lo, hi in b]
+            assert max(loads) - counts.sum() / world <= counts.max()               # balanced within one slide
+    # the TCGA-scale config: 1000 slides x 2000 tiles over 8 GPUs -> 125 slides each
+    assert bdist.shard_bounds([2000] * 1000, 8) == [(125 * r, 125 * (r + 1)) for r in range(8)]
+
+
+def test_all_gather_groups_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    df = synth.tile_table(n_slides=11, tiles_per_slide=40, seed=21, ragged=True)
+    names, gp, gu, gt, cnt, first = _local_groups(df)
+    for r in range(world):
+        g = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(g["code"], np.arange(len(names)))
+        assert np.array_equal(g["count"], cnt)
+        assert g["y_pred"].tobytes() == gp.tobytes()                # bit-exact: slides never straddle ranks
+        assert g["uncertainty"].tobytes() == gu.tobytes()
+        assert np.array_equal(g["y_true"], gt.astype(np.uint8))
+
+
+def test_single_process_passthrough():
+    msg = bdist.pack_groups(0, [3, 0, 2], [0, -1, 5], 0, np.float32([.1, np.nan, .3]), np.float32([.01, np.nan, .03]),
+                            [0.0, np.nan, 1.0])
+    out = bdist.unpack_groups(bdist.all_gather_groups(msg), np.float32)
+    assert list(out["code"]) == [0, 2] and list(out["y_true"]) == [0, 1]

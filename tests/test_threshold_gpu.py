@@ -193,3 +193,14 @@ def test_config5_full_size_properties(T):
     perm = dfs[1].sample(frac=1.0, random_state=0).reset_index(drop=True)
     pa = T.detect(perm)[0]
     assert pa["tile_uq"] == per[1]["tile_uq"] and pa["tile_pred"] == per[1]["tile_pred"]
+
+
+def test_apply_sharded_single_rank_equals_apply(T):
+    for kw in (dict(n_slides=20, tiles_per_slide=60, seed=31), dict(n_slides=14, tiles_per_slide=45, seed=32, ragged=True)):
+        df = synth.tile_table(**kw)
+        th = dict(tile_uq=0.05, slide_uq=np.float64(0.031), tile_pred=0.5, slide_pred=0.47)
+        a, b = df.copy(), df.copy()
+        x, y = O.apply(a, **th), T.apply_sharded(b, **th)
+        assert_same_results(x[0], y[0])
+        assert_same_df(x[1], y[1])
+        assert_same_df(a, b)
