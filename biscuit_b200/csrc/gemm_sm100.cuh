@@ -38,6 +38,7 @@ struct GemmParams {
   int ldr = 0;
   __nv_bfloat16* out = nullptr;              // [M, ldc]
   int ldc = 0;
+  int out_row_off = 0;     // TMA-store epilogues: rows are written at (row + out_row_off) of the output tensor map
   int relu = 0;
   // implicit 3x3 valid convolution (conv_mode = 1): virtual row m = img*in_hw + y*in_w + x
   int conv_mode = 0;
@@ -371,7 +372,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (leader) tma_store_wait_read0();       // the previous chunk's store has finished reading its buffer
           epi_barrier();
           if (leader) {
-            tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n, m0);
+            tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n, m0 + p.out_row_off);
             tma_store_commit();
             if (has_res) {
               // prefetch the residual chunk of the NEXT epilogue step into the other buffer (its last readers
@@ -416,7 +417,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           if (row_ok) {
             const int n = n0 + c;
-            __nv_bfloat16* optr = p.out + orow * p.ldc + n;
+            __nv_bfloat16* optr = p.out + (orow + p.out_row_off) * p.ldc + n;
             const __nv_bfloat16* rptr = p.residual ? p.residual + orow * p.ldr + n : nullptr;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -731,7 +732,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (leader) tma_store_wait_read0();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
-          tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n0 + c, m0);
+          tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n0 + c, m0 + p.out_row_off);
           tma_store_commit();
           if (has_res) {
             int nt = tile, nc = c + kEpiCols;
@@ -796,7 +797,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
   if (p.shift) v = __fadd_rn(v, p.shift[n]);
   if (p.residual) v = __fadd_rn(v, __bfloat162float(p.residual[orow * p.ldr + n]));
   if (p.relu) v = fmaxf(v, 0.f);
-  p.out[orow * p.ldc + n] = __float2bfloat16_rn(v);
+  p.out[(orow + p.out_row_off) * p.ldc + n] = __float2bfloat16_rn(v);
 }
 
 }  // namespace bq

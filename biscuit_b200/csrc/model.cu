@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "layers.cuh"
+#include "head_sm100.cuh"
 
 using bq::bf16;
 using bq::GemmParams;
@@ -217,6 +218,7 @@ struct bq_model {
   bool dw_v1 = false;
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
+  bool head_fused = true;
   int max_batch = 0;
   int px = 299;
 
@@ -248,6 +250,7 @@ struct bq_model {
   struct HeadGemm { GemmParams gp; CUtensorMap ta, tb, tc, tb2; };
   std::vector<HeadGemm> head_gemms;
   int head_T = -1;
+  int head_batch = 0;                          // tiles accumulated before one fused-head launch (>= max_batch)
 
   int profiling = 0;                           // 0 off, 1 per stage, 2 per kernel family
   cudaEvent_t ev[9] = {};
@@ -364,6 +367,9 @@ int make_gemm(bq_model* m, Op& op, const bf16* a, int rows_per_tile, const PwWei
 int build_plan(bq_model* m) {
   bq_ctx* ctx = m->ctx;
   const int B = m->max_batch;
+  // the fused head is launched once per `head_batch` tiles so that it has >= 148 four-tile groups to spread over the SMs
+  m->head_batch = m->head_fused ? ((592 + B - 1) / B) * B : B;
+  if (m->head_batch < B) m->head_batch = B;
   const int px = m->px;
   const int s1 = (px - 3) / 2 + 1;        // 149
   const int s2 = s1 - 2;                  // 147
@@ -379,8 +385,8 @@ int build_plan(bq_model* m) {
       (rc = bq_alloc(ctx, m->tiles_dev2, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
       (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
       (rc = bq_alloc(ctx, m->feat_bf16, (size_t)B * kFeatures * 2)) ||
-      (rc = bq_alloc(ctx, m->out_mean, (size_t)B * m->cfg.n_classes * 4)) ||
-      (rc = bq_alloc(ctx, m->out_std, (size_t)B * m->cfg.n_classes * 4)))
+      (rc = bq_alloc(ctx, m->out_mean, (size_t)m->head_batch * m->cfg.n_classes * 4)) ||
+      (rc = bq_alloc(ctx, m->out_std, (size_t)m->head_batch * m->cfg.n_classes * 4)))
     return rc;
 
   m->plan.clear();
@@ -581,7 +587,8 @@ int prepare_head(bq_model* m, int T) {
   if (m->head_T == T) return BQ_OK;
   const int B = m->max_batch, Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers;
   int rc;
-  const size_t rows = (size_t)B * T;
+  size_t rows = (size_t)B * T;
+  if (rows < (size_t)m->head_batch) rows = (size_t)m->head_batch;
   if (T > m->head_T_cap) {
     BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto& h : m->h_act) { h.release(); if ((rc = bq_alloc(ctx, h, rows * Wd * 2 + 1024))) return rc; }
@@ -602,6 +609,11 @@ int prepare_head(bq_model* m, int T) {
     rc = make_gemm(m, op, a, 1, w, out, 1, nullptr, i == 0 ? 1.0f : inv_keep);
     m->max_batch = B;
     if (rc) return rc;
+    if (i == 0) {   // layer-0 output map spans the whole head batch: micro-batches land at their row offset
+      if ((rc = make_tmap(ctx, &op.tc, out, (uint64_t)(m->head_batch > B ? m->head_batch : B), (uint64_t)w.cout,
+                          (uint64_t)w.cout, 128, 64)))
+        return rc;
+    }
     m->head_gemms[i].gp = op.gp;
     m->head_gemms[i].ta = op.ta;
     m->head_gemms[i].tb = op.tb;
@@ -612,7 +624,10 @@ int prepare_head(bq_model* m, int T) {
   return BQ_OK;
 }
 
-int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, const uint8_t* masks_dev) {
+// phase 1 (per micro-batch): hidden_0 on the pooled features, written at row `h1_off` of the head buffer.
+// phase 2 (`n_head` > 0): the dropout-bearing layers for the n_head tiles accumulated so far.
+int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, const uint8_t* masks_dev, int h1_off = 0,
+             int n_head = -1) {
   bq_ctx* ctx = m->ctx;
   const int Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers, NC = m->cfg.n_classes;
   const uint32_t thresh = (uint32_t)floor((double)m->cfg.dropout * 4294967296.0);
@@ -623,12 +638,16 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     const int64_t cap = (int64_t)ctx->num_sms * 32;
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
   };
+  const bool fused = m->head_fused && Hn == 2 && Wd <= bq::head::kHMaxW && Wd % 64 == 0;
   for (int i = 0; i < Hn; ++i) {
     auto& hg = m->head_gemms[i];
     GemmParams g = hg.gp;
     if (i == 0) {
       g.M = nb;
+      g.out_row_off = h1_off;
+      if (nb == 0) continue;
     } else {
+      if (fused) break;
       // dropout site i: masked copy of the previous activation, one row per (tile, sample)
       const bf16* src = (const bf16*)m->h_act[(i - 1) & 1].p;
       const int per_sample = i >= 2;     // layer-1 input is per tile, deeper inputs are already per sample
@@ -643,6 +662,32 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     }
     KScope ks(m, BQ_K_HEAD_GEMM, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
     if ((rc = launch_gemm(m, g, hg.ta, hg.tb, hg.tc, hg.tc, 64, &hg.tb2))) return rc;
+  }
+  if (fused && n_head < 0) n_head = nb;
+  if (fused && n_head == 0) return BQ_OK;
+  if (fused) {
+    nb = n_head;
+    // ONE kernel: Philox masks -> hidden_1 (tcgen05) -> bias/ReLU -> mask -> prelogits -> softmax -> mean/std over T
+    bq::head::HeadParams hp;
+    hp.h1 = (const bf16*)m->h_act[0].p;
+    hp.b2 = (const float*)m->hidden[1]->shift.p;
+    hp.w3 = (const float*)m->w3.p;
+    hp.b3 = (const float*)m->b3.p;
+    hp.mean = (float*)m->out_mean.p;
+    hp.stdv = (float*)m->out_std.p;
+    hp.masks = masks_dev;
+    hp.n = nb; hp.T = T; hp.W = Wd; hp.C = NC;
+    hp.n_sites = Hn; hp.slot1 = 0; hp.slot2 = 1;
+    hp.inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+    hp.thresh = thresh;
+    hp.seed = seed; hp.tile_base = tile_base;
+    const int groups = (nb + 3) / 4;
+    const int grid = groups < ctx->num_sms ? groups : ctx->num_sms;
+    KScope ks(m, BQ_K_HEAD_FUSED, 2.0 * nb * T * Wd * (Wd + NC), 2.0 * nb * Wd + 2.0 * Wd * Wd + 8.0 * nb * NC);
+    bq::head::mc_head_fused_kernel<<<grid, bq::head::kHThreads, bq::head::HeadSmem::kTotal, ctx->stream>>>(
+        m->head_gemms[1].tb, hp);
+    BQ_LAUNCH_CHECK(ctx);
+    return BQ_OK;
   }
   const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
   const int Teff = Hn == 1 ? 1 : T;
@@ -689,6 +734,11 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->gemm_2cta = !(g && (strcmp(g, "1cta") == 0 || strcmp(g, "direct") == 0));   // default: cta_group::2 pairs
   cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::sm100::SmemPlan2::kTotal);
+  const char* hv = getenv("BQ_HEAD");
+  m->head_fused = !(hv && strcmp(hv, "unfused") == 0) &&   // debug switch: three-kernel head (expand / GEMM / final)
+                  cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
+  cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::head::HeadSmem::kTotal);
   const char* dwv = getenv("BQ_DW");
   m->dw_v1 = dwv && strcmp(dwv, "v1") == 0;    // debug switch: first-generation depthwise kernel
   cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -811,9 +861,11 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
   const size_t mask_per_tile = (size_t)T * Hn * Wd;
   const bool masks_on_dev = masks && bq_is_device_ptr(masks);
   if (masks && !masks_on_dev) {
-    int rc = bq_alloc(ctx, m->masks_dev, (size_t)B * mask_per_tile);
+    int rc = bq_alloc(ctx, m->masks_dev, (size_t)m->head_batch * mask_per_tile);
     if (rc) return rc;
   }
+  int64_t head_start = 0;      // first tile of the head batch being accumulated
+  int head_count = 0;
   if (m->profiling) for (auto& s : m->stage_ms) s = 0.f;
   if (m->profiling == 2)
     for (int k = 0; k < BQ_PROFILE_KINDS; ++k) { m->k_ms[k] = m->k_flops[k] = m->k_bytes[k] = 0; m->k_launches[k] = 0; }
@@ -845,24 +897,44 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
       BQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copied[slot], 0));
       m->tiles_src = stage[slot];
     }
-    const uint8_t* mdev = nullptr;
+    const uint8_t* mdev = nullptr;       // masks of the head batch (device)
     if (masks) {
-      if (masks_on_dev) mdev = masks + (size_t)i0 * mask_per_tile;
+      if (masks_on_dev) mdev = masks + (size_t)head_start * mask_per_tile;
       else {
-        BQ_CUDA(ctx, cudaMemcpyAsync(m->masks_dev.p, masks + (size_t)i0 * mask_per_tile, (size_t)nb * mask_per_tile,
+        BQ_CUDA(ctx, cudaMemcpyAsync((uint8_t*)m->masks_dev.p + (size_t)head_count * mask_per_tile,
+                                     masks + (size_t)i0 * mask_per_tile, (size_t)nb * mask_per_tile,
                                      cudaMemcpyHostToDevice, ctx->stream));
         mdev = (const uint8_t*)m->masks_dev.p;
       }
     }
     if ((rc = run_backbone(m, nb, nullptr, nullptr))) return rc;
     if (!tiles_on_dev) BQ_CUDA(ctx, cudaEventRecord(m->consumed[slot], ctx->stream));
-    if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0, mdev))) return rc;
-    if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
-    if ((rc = bq_from_device(ctx, mean + (size_t)i0 * NC, m->out_mean.p, (size_t)nb * NC * 4)) ||
-        (rc = bq_from_device(ctx, std + (size_t)i0 * NC, m->out_std.p, (size_t)nb * NC * 4)))
-      return rc;
     if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
       return rc;
+    const bool last = i0 + B >= n;
+    if (m->head_fused) {
+      // hidden_0 now (per micro-batch); the dropout-bearing layers once enough tiles are queued to fill the SMs
+      if ((rc = run_head(m, nb, T, seed, 0, nullptr, head_count, 0))) return rc;
+      head_count += nb;
+      if (last || head_count + B > m->head_batch) {
+        if ((rc = run_head(m, 0, T, seed, tile_index_base + (uint64_t)head_start, mdev, 0, head_count))) return rc;
+        if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
+        if ((rc = bq_from_device(ctx, mean + (size_t)head_start * NC, m->out_mean.p, (size_t)head_count * NC * 4)) ||
+            (rc = bq_from_device(ctx, std + (size_t)head_start * NC, m->out_std.p, (size_t)head_count * NC * 4)))
+          return rc;
+        head_start += head_count;
+        head_count = 0;
+      } else if (m->profiling) {
+        cudaEventRecord(m->ev[6], ctx->stream);
+      }
+    } else {
+      if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0, mdev))) return rc;
+      if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
+      if ((rc = bq_from_device(ctx, mean + (size_t)i0 * NC, m->out_mean.p, (size_t)nb * NC * 4)) ||
+          (rc = bq_from_device(ctx, std + (size_t)i0 * NC, m->out_std.p, (size_t)nb * NC * 4)))
+        return rc;
+      head_start = i0 + nb;
+    }
     kprofile_collect(m);
     if (m->profiling) {
       BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -171,3 +171,36 @@ def test_simt_debug_path_agrees():
     print("simt vs tcgen05: max d (mean/std)", np.abs(a[:8] - b[:8]).max(), "features", np.abs(a[8:] - b[8:]).max())
     assert np.abs(a[:8] - b[:8]).max() <= 3e-3
     assert np.abs(a[8:] - b[8:]).max() <= 2e-2 * np.abs(a[8:]).max()
+
+
+@pytest.mark.parametrize("t_samples", [7, 32, 70])
+def test_fused_head_sample_chunks_vs_oracle(iface, tiles, oracle_bf16, t_samples):
+    """T < 32, T == 32 and T > 32 (sample chunks merged with Chan's formula) against the oracle head"""
+    o, _, _ = oracle_bf16
+    masks = X.keep_masks(N_TILES, t_samples, 1024, 0.1, 77)
+    mean, std = iface.predict(tiles, T=t_samples, masks=masks)
+    m_ref, s_ref = o.predict_uq(tiles, T=t_samples, masks=masks)
+    assert np.abs(mean - m_ref).max() <= 4e-3 and np.abs(std - s_ref).max() <= 4e-3
+    a = iface.predict(tiles, T=t_samples, seed=77)
+    assert np.array_equal(a[0], mean) and np.array_equal(a[1], std)      # Philox == injected masks
+
+
+def test_unfused_head_debug_path_agrees():
+    """BQ_HEAD=unfused (expand + GEMM + final kernels) vs the default single fused head kernel"""
+    code = (
+        "import numpy as np, sys\n"
+        "from oracle import synth\n"
+        "from biscuit_b200.weights import random_init\n"
+        "from biscuit_b200.uq import UncertaintyInterface\n"
+        "i = UncertaintyInterface(random_init(seed=1), max_batch=3)\n"
+        "m, s = i.predict(synth.tiles_u8(5, seed=0), T=30, seed=5)\n"
+        "np.save(sys.argv[1], np.concatenate([m.ravel(), s.ravel()]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("unfused", "fused"):
+        path = f"/tmp/bq_head_{mode}.npy"
+        env = dict(os.environ, BQ_HEAD=mode, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
+        outs.append(np.load(path))
+    print("unfused vs fused head: max d", np.abs(outs[0] - outs[1]).max())
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-4
