@@ -105,7 +105,7 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
              const float* __restrict__ w /*[27][32]*/, const float* __restrict__ scale, const float* __restrict__ shift,
              bf16* __restrict__ out, int in_px, int out_px) {
   __shared__ float patch[kC1In * kC1In * 3];
-  __shared__ float ws[27 * 32];
+  __shared__ __align__(16) float ws[27 * 32];
   __shared__ float sc[32], sh[32];
   const int img = blockIdx.z;
   const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
@@ -125,9 +125,10 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
   const int ty = threadIdx.x / kC1Tile, tx = threadIdx.x % kC1Tile;
   const int oy = oy0 + ty, ox = ox0 + tx;
   if (oy >= out_px || ox >= out_px) return;
-  float acc[32];
+  // 27 inputs x 32 channels: weights as LDS.128 broadcasts, packed fp32x2 FMAs (FFMA2) -- same per-lane RN fma
+  float2 acc2[16];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int c = 0; c < 16; ++c) acc2[c] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -135,12 +136,20 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float x = patch[((2 * ty + ky) * kC1In + (2 * tx + kx)) * 3 + ci];
-        const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * 32;
+        const float2 xx = make_float2(x, x);
+        const float4* wr = (const float4*)(ws + ((ky * 3 + kx) * 3 + ci) * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wv = wr[c4];
+          acc2[2 * c4] = __ffma2_rn(xx, make_float2(wv.x, wv.y), acc2[2 * c4]);
+          acc2[2 * c4 + 1] = __ffma2_rn(xx, make_float2(wv.z, wv.w), acc2[2 * c4 + 1]);
+        }
       }
     }
   }
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { acc[2 * c] = acc2[c].x; acc[2 * c + 1] = acc2[c].y; }
   bf16* o = out + (((int64_t)img * out_px + oy) * out_px + ox) * 32;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -210,13 +219,13 @@ depthwise3x3_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[
 // ---------------------------------------------------------------------------------------------------
 constexpr int kDwTile = 19;
 constexpr int kDwHalo = kDwTile + 2;
-__device__ __forceinline__ void dw_load3(const bf16* row, int CC, float (&d)[3][4]) {
+// three horizontally adjacent pixels x 4 channels, widened to fp32 as two float2 pairs (for FFMA2)
+__device__ __forceinline__ void dw_load3(const bf16* row, int CC, float2 (&d)[3][2]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint2 v = *(const uint2*)(row + (size_t)k * CC);
-    const __nv_bfloat162* b = (const __nv_bfloat162*)&v;
-    const float2 f01 = __bfloat1622float2(b[0]), f23 = __bfloat1622float2(b[1]);
-    d[k][0] = f01.x; d[k][1] = f01.y; d[k][2] = f23.x; d[k][3] = f23.y;
+    d[k][0] = make_float2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u));
+    d[k][1] = make_float2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
   }
 }
 __global__ void __launch_bounds__(320)
@@ -247,12 +256,13 @@ depthwise3x3_smem_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W
   const int c4 = threadIdx.x % cpc, px = threadIdx.x / cpc;      // blockDim = cpc * kDwTile
   const int th = min(kDwTile, H - ty0), tw = min(kDwTile, W - tx0);
   const bool active = px < tw;
-  float wr[9][4];
+  float2 wr[9][2];                                               // 9 taps x 4 channels as float2 pairs
   if (active) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 wv = __ldg((const float4*)(w + (int64_t)t * C + c0 + c4 * 4));
-      wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
+      wr[t][0] = make_float2(wv.x, wv.y);
+      wr[t][1] = make_float2(wv.z, wv.w);
     }
   }
   __syncthreads();                                               // barrier initialised before anyone polls it
@@ -284,28 +294,24 @@ depthwise3x3_smem_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W
   const bf16* col = tile + (size_t)px * CC + c4 * 4;             // halo column px (= image column px - 1)
   const size_t row_stride = (size_t)kDwHalo * CC;
   bf16* dst = out + ((int64_t)img * H * W + (int64_t)ty0 * W + tx0 + px) * C + c0 + c4 * 4;
-  float ra[3][4], rb[3][4], rc[3][4];                            // rolling window rows (static register names)
+  float2 ra[3][2], rb[3][2], rc[3][2];                           // rolling window rows (static register names)
   dw_load3(col, CC, ra);
   dw_load3(col + row_stride, CC, rb);
-  auto step = [&](const float (&r0)[3][4], const float (&r1)[3][4], float (&r2)[3][4], int py) {
+  // packed fp32x2 FMAs (Blackwell FFMA2): two channels per instruction, each lane an ordinary RN fma, so the
+  // result is bit-identical to 36 scalar fmaf in the same tap order
+  auto step = [&](const float2 (&r0)[3][2], const float2 (&r1)[3][2], float2 (&r2)[3][2], int py) {
     dw_load3(col + (size_t)(py + 2) * row_stride, CC, r2);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
+    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r0[kx][0], wr[kx][0], a0); a1 = __ffma2_rn(r0[kx][1], wr[kx][1], a1); }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(r0[kx][j], wr[kx][j], acc[j]);
+    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r1[kx][0], wr[3 + kx][0], a0); a1 = __ffma2_rn(r1[kx][1], wr[3 + kx][1], a1); }
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(r1[kx][j], wr[3 + kx][j], acc[j]);
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(r2[kx][j], wr[6 + kx][j], acc[j]);
+    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r2[kx][0], wr[6 + kx][0], a0); a1 = __ffma2_rn(r2[kx][1], wr[6 + kx][1], a1); }
     uint2 o;
     __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-    ob[0] = __floats2bfloat162_rn(acc[0], acc[1]);
-    ob[1] = __floats2bfloat162_rn(acc[2], acc[3]);
+    ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
+    ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
     *(uint2*)(dst + (int64_t)py * W * C) = o;
   };
   for (int py = 0; py < th; py += 3) {

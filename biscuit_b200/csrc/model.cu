@@ -219,6 +219,7 @@ struct bq_model {
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
+  int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
   int max_batch = 0;
   int px = 299;
 
@@ -484,7 +485,7 @@ int build_plan(bq_model* m) {
   return dw_rc;
 }
 
-int run_op(bq_model* m, Op& op, int nb) {
+int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
   bq_ctx* ctx = m->ctx;
   const int px = m->px;
   auto grid1d = [&](int64_t total) {
@@ -538,7 +539,7 @@ int run_op(bq_model* m, Op& op, int nb) {
     case OP_POOLADD: {
       KScope ks(m, BQ_K_POOLADD, 0, act * nb * op.C * ((double)op.H * op.W + 2.0 * op.Ho * op.Wo));
       bq::maxpool_add_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
-          op.in, op.in2, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left);
+          op.in, op.in2, op.out + out_off, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left);
       break;
     }
     case OP_SUBSAMPLE: {
@@ -566,14 +567,41 @@ int stage_tiles(bq_model* m, const uint8_t* tiles, int nb) {
   return BQ_OK;
 }
 
+// The entry flow (block1..block4: 147^2..37^2 maps, 5.5 MB of activations per tile and layer) runs in SUB-batches of
+// `entry_batch` tiles that reuse the same arena addresses, so its intermediates stay L2-resident (126 MB) instead of
+// streaming through HBM; the middle / exit flow (19^2 maps, 0.5 MB per tile) runs on the whole micro-batch so that its
+// GEMMs have enough tiles to fill the 74 CTA pairs.
 int run_backbone(bq_model* m, int nb, const std::string* stop_tag, const Op** stopped) {
+  const size_t tile_bytes = (size_t)m->px * m->px * 3;
+  const uint8_t* src0 = m->tiles_src;
+  size_t entry_end = 0;
+  while (entry_end < m->plan.size() && m->plan[entry_end].stage <= 2) ++entry_end;
+  const int EB = (stop_tag || m->entry_batch <= 0 || m->entry_batch > nb) ? nb : m->entry_batch;
   int cur_stage = -1;
-  for (auto& op : m->plan) {
+  for (int sub0 = 0; sub0 < nb; sub0 += EB) {
+    const int nsub = (nb - sub0 < EB) ? (nb - sub0) : EB;
+    m->tiles_src = src0 + (size_t)sub0 * tile_bytes;
+    for (size_t i = 0; i < entry_end; ++i) {
+      Op& op = m->plan[i];
+      if (m->profiling && sub0 == 0 && op.stage != cur_stage) {
+        cudaEventRecord(m->ev[op.stage], m->ctx->stream);
+        cur_stage = op.stage;
+      }
+      // the last entry op (block4 pool+add) scatters each sub-batch to its rows of the full micro-batch tensor
+      const int64_t out_off = (i + 1 == entry_end) ? (int64_t)sub0 * op.Ho * op.Wo * op.C : 0;
+      int rc = run_op(m, op, nsub, out_off);
+      if (rc) { m->tiles_src = src0; return rc; }
+      if (stop_tag && op.tag == *stop_tag) { if (stopped) *stopped = &op; m->tiles_src = src0; return BQ_OK; }
+    }
+  }
+  m->tiles_src = src0;
+  for (size_t i = entry_end; i < m->plan.size(); ++i) {
+    Op& op = m->plan[i];
     if (m->profiling && op.stage != cur_stage) {
       cudaEventRecord(m->ev[op.stage], m->ctx->stream);
       cur_stage = op.stage;
     }
-    int rc = run_op(m, op, nb);
+    int rc = run_op(m, op, nb, 0);
     if (rc) return rc;
     if (stop_tag && op.tag == *stop_tag) { if (stopped) *stopped = &op; return BQ_OK; }
   }
@@ -739,6 +767,8 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
   cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::head::HeadSmem::kTotal);
+  const char* eb = getenv("BQ_ENTRY_BATCH");
+  if (eb) m->entry_batch = atoi(eb);
   const char* dwv = getenv("BQ_DW");
   m->dw_v1 = dwv && strcmp(dwv, "v1") == 0;    // debug switch: first-generation depthwise kernel
   cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Developer helper (run under gpurun): throughput vs backbone micro-batch size.
-for b in 16 32 64 128; do
+for b in ${BATCHES:-64 128 256 512}; do
   echo "=== max_batch $b"
-  timeout 300 python bench.py --tiles 2048 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --max-batch $b 2>&1 | tail -1 | \
+  timeout 300 python bench.py --tiles 4096 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --max-batch $b 2>&1 | tail -1 | \
     python -c "import sys,json; d=json.loads(sys.stdin.read()); print('tiles/s %.0f'%d['value']); [print('  %-16s %8.2f ms  %7.1f TF  %7.0f GB/s  x%d'%(k,v['ms'],v['tflops'],v['gbs'],v['launches'])) for k,v in d['kernels'].items() if v['ms']>2]"
 done
