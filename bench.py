@@ -132,6 +132,10 @@ def cpu_reference_step(oracle, tiles, T, seed):
 
 def make_cpu_oracle():
     import torch
+    try:                      # torchrun pins OMP_NUM_THREADS=1: the CPU arm uses every core this process may run on
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     from biscuit_b200.weights import random_init
     from oracle import xception_uq as X          # CPU-baseline leg: the one place bench.py may touch oracle/
     return X.XceptionUQOracle(random_init(seed=1), emulate_bf16=False), torch.get_num_threads()
