@@ -75,6 +75,7 @@ SIGNATURES = {
                                        C.c_int64, C.POINTER(C.c_int64)]),
     "bq_model_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bq_model_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bq_debug_umma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bq_model_kernel_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

@@ -555,7 +555,7 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                          const GemmParams p) {
@@ -763,7 +763,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }  // namespace sm100
 
 // ---- debug-only SIMT GEMM with the same parameter block (BQ_GEMM=simt); slow, obviously correct ----
-__global__ void gemm_simt_kernel(const GemmParams p) {
+static __global__ void gemm_simt_kernel(const GemmParams p) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;

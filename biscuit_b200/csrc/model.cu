@@ -16,6 +16,7 @@
 #include "gemm_sm100.cuh"
 #include "layers.cuh"
 #include "head_sm100.cuh"
+#include "dw_sm100.cuh"
 
 using bq::bf16;
 using bq::GemmParams;
@@ -67,7 +68,7 @@ int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uin
 
 // 4-D NHWC bf16 activation [N, H, W, C] with a [1, box_h, box_w, box_c] box, no swizzle (depthwise halo tiles)
 int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
-                   uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c, bool swizzle128 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {c, w, h, n};
@@ -75,8 +76,8 @@ int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, u
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
   return BQ_OK;
 }
@@ -91,6 +92,7 @@ struct PwWeights {          // a GEMM's B operand + per-channel epilogue
 };
 struct SepWeights {
   DevBuf dw;                // fp32 [9][cin]
+  DevBuf bdiag;             // bf16 [ceil(cin/64)][9 taps][4 groups][16x16 diagonal tile] for the tensor-core depthwise
   PwWeights pw;
 };
 
@@ -195,6 +197,7 @@ struct Op {
   int H = 0, W = 0, C = 0, Ho = 0, Wo = 0, Cout = 0;
   int relu_in = 0, pad_top = 0, pad_left = 0;
   const float* dw = nullptr;
+  const bf16* bdiag = nullptr;
   // gemm
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
@@ -215,7 +218,7 @@ struct bq_model {
   bq_model_config cfg{};
   bool weights_loaded = false;
   bool use_simt = false;
-  bool dw_v1 = false;
+  int dw_mode = 1;                             // 1: smem + FFMA2 sliding window (default), 2: tensor-core depthwise, 0: first generation
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
@@ -424,6 +427,11 @@ int build_plan(bq_model* m) {
     const int CC = (c % 64 == 0) ? 64 : 56;
     int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::kDwHalo, bq::kDwHalo, CC);
     if (r && !dw_rc) dw_rc = r;
+    r = make_tmap_nhwc(ctx, &op.tb, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kHalo, bq::dwtc::kHalo, 64, true);
+    if (r && !dw_rc) dw_rc = r;
+    r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kTile, bq::dwtc::kTile, 64, true);
+    if (r && !dw_rc) dw_rc = r;
+    op.bdiag = (const bf16*)sw.bdiag.p;
     m->plan.push_back(op);
   };
   auto add_gemm = [&](const bf16* a, int rows, const PwWeights& w, bf16* out, int relu, const bf16* resid, int stage,
@@ -522,7 +530,16 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
     }
     case OP_DW: {
       KScope ks(m, BQ_K_DW, 2.0 * 9 * nb * op.H * op.W * op.C, 2 * act * nb * op.H * op.W * op.C);
-      if (m->dw_v1) {
+      if (m->dw_mode == 2) {
+        const int tiles = (op.H + bq::dwtc::kTile - 1) / bq::dwtc::kTile;
+        const int chunks = (op.C + 63) / 64;
+        int per_chunk = ctx->num_sms / chunks;                       // CTAs per channel chunk (persistent)
+        const int items = nb * tiles * tiles;
+        if (per_chunk > items) per_chunk = items;
+        if (per_chunk < 1) per_chunk = 1;
+        bq::dwtc::depthwise3x3_tc_kernel<<<chunks * per_chunk, bq::dwtc::kThreads, bq::dwtc::kSmem, ctx->stream>>>(
+            op.tb, op.tc, op.bdiag, nb, op.H, op.W, op.C, tiles, chunks, op.relu_in);
+      } else if (m->dw_mode == 0) {
         bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
             op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
       } else {
@@ -770,7 +787,8 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   const char* eb = getenv("BQ_ENTRY_BATCH");
   if (eb) m->entry_batch = atoi(eb);
   const char* dwv = getenv("BQ_DW");
-  m->dw_v1 = dwv && strcmp(dwv, "v1") == 0;    // debug switch: first-generation depthwise kernel
+  m->dw_mode = dwv && strcmp(dwv, "v1") == 0 ? 0 : (dwv && strcmp(dwv, "tc") == 0 ? 2 : 1);   // experiment switches
+  cudaFuncSetAttribute(bq::dwtc::depthwise3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwtc::kSmem);
   cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::kDwHalo * bq::kDwHalo * 64 * (int)sizeof(bf16));
   for (auto& e : m->ev) cudaEventCreate(&e);
@@ -828,7 +846,29 @@ int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n
     const bq_named_tensor* d;
     int r;
     if ((r = need(ctx, ti, name + "/depthwise_kernel", {3, 3, cin, 1}, &d))) return r;
-    if ((r = upload(ctx, s->dw, d->data, (size_t)9 * cin * 4))) return r;
+    {
+      // depthwise weights are bf16 operands of the tensor-core kernel; the CUDA-core debug kernels use the same
+      // (bf16-rounded) values widened to fp32 so that every path computes the same function
+      std::vector<float> dwr((size_t)9 * cin);
+      for (size_t i = 0; i < dwr.size(); ++i) {
+        const uint32_t u = (uint32_t)f32_to_bf16_rne(d->data[i]) << 16;
+        memcpy(&dwr[i], &u, 4);
+      }
+      if ((r = upload(ctx, s->dw, dwr.data(), dwr.size() * 4))) return r;
+    }
+    {
+      const int chunks = (cin + 63) / 64;
+      std::vector<uint16_t> bd((size_t)chunks * 36 * 256, 0);
+      for (int ch = 0; ch < chunks; ++ch)
+        for (int tp = 0; tp < 9; ++tp)
+          for (int cg = 0; cg < 4; ++cg)
+            for (int n = 0; n < 16; ++n) {
+              const int c = ch * 64 + cg * 16 + n;
+              if (c < cin)
+                bd[((size_t)ch * 36 + tp * 4 + cg) * 256 + bq::dwtc::bdiag_index(n, n)] = f32_to_bf16_rne(d->data[(size_t)tp * cin + c]);
+            }
+      if ((r = upload(ctx, s->bdiag, bd.data(), bd.size() * 2))) return r;
+    }
     if ((r = load_conv_gemm(ctx, ti, name, "pointwise_kernel", 1, cin, cout, s->pw))) return r;
     m->sep[name] = std::move(s);
     return BQ_OK;

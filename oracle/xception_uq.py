@@ -139,7 +139,8 @@ class XceptionUQOracle:
             else:
                 dw = self.w[f"{name}/depthwise_kernel"].permute(2, 3, 0, 1).contiguous()   # [C,1,3,3] fp32
                 pw = self.w[f"{name}/pointwise_kernel"].permute(3, 2, 0, 1).contiguous()
-                self.conv[name] = (dw, q(pw)) + self._bn(f"{name}_bn")
+                # depthwise weights are bf16 tensor-core operands on the CUDA path (fp32 in the fp32 tier)
+                self.conv[name] = (q(dw), q(pw)) + self._bn(f"{name}_bn")
 
     # ---- pre-processing: tf.image.per_image_standardization (results.py:255)
     @staticmethod
