@@ -760,6 +760,155 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
+// =====================================================================================================
+// block1_conv2 (3x3 valid, 32 -> 64) as an INPUT-STATIONARY implicit GEMM.
+// The first implementation re-fetched a 128x32 A tile per filter tap (nine L2 round trips per output tile, L2 bound at
+// ~195 TFLOP/s).  Here the producer loads ONE window of the activation matrix per M tile -- the 128 virtual rows plus the
+// 2*W+2 rows the taps reach forward to (4 TMA boxes of 128 rows, 64-byte swizzle) -- and every tap is the SAME smem window
+// with the A descriptor start advanced by (ky*W + kx) rows of 64 bytes.  tcgen05 swizzles on absolute smem address bits, so
+// row-shifted descriptors are exact (profiles/umma_probe.py).  The nine 64x32 weight tiles stay resident for the whole
+// persistent CTA.  18 MMAs (128x64x16) per tile, four TMEM accumulator stages.
+// =====================================================================================================
+constexpr int kC2Stages = 3;
+constexpr int kC2WinRows = 512;                          // 4 boxes x 128 rows >= 128 + 2*149 + 2
+constexpr int kC2WinBytes = kC2WinRows * 64;             // 32 KB
+constexpr int kC2BBytes = 9 * 64 * 64;                   // 36 KB: nine taps x [64 n][32 k] bf16
+constexpr int kC2AccStages = 4;
+constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + 256 + 1024;
+
+static __global__ void __launch_bounds__(kThreads, 1)
+conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [128 x 32] SW64*/,
+                  const __grid_constant__ CUtensorMap tmap_b /*[64, 288] box [64 x 32] SW64*/, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_smem = smem_base, win0 = smem_base + kC2BBytes;
+  const uint32_t bar_base = win0 + kC2Stages * kC2WinBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kC2Stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kC2Stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kC2Stages + kC2AccStages + a); };
+  const uint32_t b_bar = bar_base + 8u * (2 * kC2Stages + 2 * kC2AccStages);
+  const uint32_t tmem_slot = b_bar + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      (volatile uint32_t*)(smem_gen + kC2BBytes + kC2Stages * kC2WinBytes + 8 * (2 * kC2Stages + 2 * kC2AccStages + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = (p.M + kBM - 1) / kBM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kC2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < kC2AccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(b_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_bar, (uint32_t)kC2BBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(b_smem + t * 4096, &tmap_b, b_bar, t * 32, 0);
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), (uint32_t)kC2WinBytes);
+        for (int b = 0; b < 4; ++b)
+          tma_load_2d(win0 + s * kC2WinBytes + b * 128 * 64, &tmap_a, full_bar(s), 0, tile * kBM + b * 128);
+        if (++s == kC2Stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(b_bar, 0);
+      const uint32_t idesc = make_idesc(kBM, 64);
+      const uint64_t b_base = make_smem_desc<64>(b_smem);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t a_base = make_smem_desc<64>(win0 + s * kC2WinBytes);
+        const uint32_t d = tmem_base + (uint32_t)(as * 64);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int roff = ((t / 3) * p.in_w + (t % 3)) * 64;           // tap = rows shifted inside the window
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(d, a_base + (uint64_t)((roff + k * 32) >> 4), b_base + (uint64_t)((t * 4096 + k * 32) >> 4), idesc,
+                      (t | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(as));
+        if (++s == kC2Stages) { s = 0; ph ^= 1u; }
+        if (++as == kC2AccStages) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int as = 0; uint32_t aph = 0;
+    // per-channel BN constants (64 channels) in registers-by-load: read once
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m = tile * kBM + quad * 32 + lane;
+      bool row_ok = m < p.M;
+      long long orow = 0;
+      if (row_ok) {
+        const int img = m / p.in_hw, rem = m - img * p.in_hw;
+        const int y = rem / p.in_w, x = rem - y * p.in_w;
+        row_ok = (y < p.out_h) && (x < p.out_w);
+        orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
+      }
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      uint32_t v[64];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 64);
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32u, v1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (row_ok) {
+        __nv_bfloat16* optr = p.out + orow * p.ldc;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 s0 = __ldg((const float4*)(p.scale + g * 8)), s1 = __ldg((const float4*)(p.scale + g * 8 + 4));
+          const float4 h0 = __ldg((const float4*)(p.shift + g * 8)), h1 = __ldg((const float4*)(p.shift + g * 8 + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
+            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4 o;
+          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *(uint4*)(optr + g * 8) = o;
+        }
+      }
+      if (++as == kC2AccStages) { as = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace sm100
 
 // ---- debug-only SIMT GEMM with the same parameter block (BQ_GEMM=simt); slow, obviously correct ----

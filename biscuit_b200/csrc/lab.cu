@@ -12,6 +12,7 @@ using namespace bq::sm100;
 
 // D[128 x 16] = A[128 x 16] * B^T, A = rows [shift, shift+128) x channels [cg*16, +16) of a [rows x 64] bf16 tile that a
 // TMA load placed in smem with SWIZZLE_128B; B = 16x16 identity in the no-swizzle K-major layout.
+template <int SWZ>
 __global__ void __launch_bounds__(128, 1)
 umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, int rows, int shift, int cg, int base_offset_mode,
                         float* __restrict__ out /*[128][16]*/) {
@@ -41,12 +42,12 @@ umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, int rows, in
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)rows * 128u);
-    for (int r0 = 0; r0 < rows; r0 += 128) tma_load_2d(tile + r0 * 128, &tmap_x, bar, 0, r0);
+    mbar_expect_tx(bar, (uint32_t)rows * (uint32_t)SWZ);
+    for (int r0 = 0; r0 < rows; r0 += 128) tma_load_2d(tile + r0 * SWZ, &tmap_x, bar, 0, r0);
     mbar_wait(bar, 0);
     tc_fence_after();
-    const uint32_t a_addr = tile + (uint32_t)shift * 128u + (uint32_t)cg * 32u;
-    uint64_t da = make_smem_desc<128>(a_addr);
+    const uint32_t a_addr = tile + (uint32_t)shift * (uint32_t)SWZ + (uint32_t)cg * 32u;
+    uint64_t da = make_smem_desc<SWZ>(a_addr);
     if (base_offset_mode == 1) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
     // B: layout none, LBO = 128 B (next 8 k), SBO = 256 B (next 8 n)
     const uint64_t db = (uint64_t)((bmat & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
@@ -67,12 +68,16 @@ umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, int rows, in
 
 extern "C" int bq_debug_umma_probe(bq_ctx* ctx, int rows, int shift, int cg, int base_offset_mode, const uint16_t* x_bf16,
                                    float* out) {
-  if (!ctx || !x_bf16 || !out || rows < 128 || rows > 384 || rows % 128 || shift < 0 || shift + 128 > rows + 0 * 128 + 256 || cg < 0 || cg > 3)
+  // base_offset_mode bit 1 selects the 64-byte-swizzle variant (rows of 32 bf16)
+  const int swz = (base_offset_mode & 2) ? 64 : 128;
+  const int cols = swz / 2;
+  base_offset_mode &= 1;
+  if (!ctx || !x_bf16 || !out || rows < 128 || rows > 384 || rows % 128 || shift < 0 || shift > 256 || cg < 0 || cg * 16 >= cols)
     return bq_fail(ctx, BQ_ERR_ARG, "bq_debug_umma_probe: bad argument");
   BQ_CUDA(ctx, cudaSetDevice(ctx->device));
   DevBuf x, o;
   int rc;
-  if ((rc = bq_to_device(ctx, x, x_bf16, (size_t)rows * 64 * 2)) || (rc = bq_alloc(ctx, o, 128 * 16 * 4))) return rc;
+  if ((rc = bq_to_device(ctx, x, x_bf16, (size_t)rows * cols * 2)) || (rc = bq_alloc(ctx, o, 128 * 16 * 4))) return rc;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
@@ -81,16 +86,18 @@ extern "C" int bq_debug_umma_probe(bq_ctx* ctx, int rows, int shift, int cg, int
                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   CUtensorMap tm;
-  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, 128};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)swz};
+  cuuint32_t box[2] = {(cuuint32_t)cols, 128};
   cuuint32_t es[2] = {1, 1};
   if (((Enc)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return bq_fail(ctx, BQ_ERR_CUDA, "tensor map encode failed");
   const int smem = 384 * 128 + 2048 + 1024;
-  cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  umma_shift_probe_kernel<<<1, 128, smem, ctx->stream>>>(tm, rows, shift, cg, base_offset_mode, (float*)o.p);
+  cudaFuncSetAttribute(umma_shift_probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(umma_shift_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (swz == 128) umma_shift_probe_kernel<128><<<1, 128, smem, ctx->stream>>>(tm, rows, shift, cg, base_offset_mode, (float*)o.p);
+  else umma_shift_probe_kernel<64><<<1, 128, smem, ctx->stream>>>(tm, rows, shift, cg, base_offset_mode, (float*)o.p);
   BQ_LAUNCH_CHECK(ctx);
   BQ_CUDA(ctx, cudaMemcpyAsync(out, o.p, 128 * 16 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

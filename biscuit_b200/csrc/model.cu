@@ -222,6 +222,7 @@ struct bq_model {
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
+  bool conv2_is = true;                        // input-stationary block1_conv2 (BQ_CONV2=taps selects the per-tap reload kernel)
   int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
   int max_batch = 0;
   int px = 299;
@@ -316,7 +317,10 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
   const int n_tiles = (gp.N + gp.bn_box - 1) / gp.bn_box;
   int grid = m_tiles * n_tiles;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
-  if (blk_k == 32) {
+  if (blk_k == 32 && m->conv2_is && gp.conv_mode && gp.N == 64 && gp.K == 288 && 2 * gp.in_w + 2 + 128 <= kC2WinRows) {
+    int g2 = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
+    conv3x3_is_kernel<<<g2, kThreads, kC2Smem, ctx->stream>>>(ta, tb, gp);
+  } else if (blk_k == 32) {
     gemm_tcgen05_kernel<32, false><<<grid, kThreads, SmemPlan<32, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
     const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
@@ -784,6 +788,9 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
   cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::head::HeadSmem::kTotal);
+  const char* c2 = getenv("BQ_CONV2");
+  m->conv2_is = !(c2 && strcmp(c2, "taps") == 0);
+  cudaFuncSetAttribute(bq::sm100::conv3x3_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sm100::kC2Smem);
   const char* eb = getenv("BQ_ENTRY_BATCH");
   if (eb) m->entry_batch = atoi(eb);
   const char* dwv = getenv("BQ_DW");
