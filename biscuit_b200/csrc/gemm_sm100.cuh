@@ -496,14 +496,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 constexpr int k2Stages = 4;
 constexpr int k2EpiWarps = 8;                        // two warps per TMEM lane quadrant (32 columns of a chunk each)
 constexpr int k2Threads = 64 + 32 * k2EpiWarps;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
-constexpr int k2MaxN = 2048;                         // per-channel scale/shift staged in smem for the whole N
+constexpr int k2MaxN = 2048;
+constexpr int k2ResBufs = 3;                         // residual chunks in flight (prefetch distance 2)                         // per-channel scale/shift staged in smem for the whole N
 struct SmemPlan2 {
   static constexpr int kABytes = kBM * 64 * 2;                 // 16 KB
   static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (half of the N tile)
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutOffset = k2Stages * kStageBytes;
   static constexpr int kResOffset = kOutOffset + 2 * kEpiBytes;
-  static constexpr int kScaleOffset = kResOffset + 2 * kEpiBytes;      // float scale[k2MaxN], shift[k2MaxN]
+  static constexpr int kScaleOffset = kResOffset + k2ResBufs * kEpiBytes;   // float scale[k2MaxN], shift[k2MaxN]
   static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
@@ -571,8 +572,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kAccStages + a); };
   auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 * kAccStages + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages + 2);
-  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + 2));
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages + k2ResBufs);
+  volatile uint32_t* tmem_slot_ptr =
+      (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + k2ResBufs));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -592,7 +594,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (p.residual) tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kAccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * k2EpiWarps); }
-    mbar_init(res_bar(0), 1); mbar_init(res_bar(1), 1);
+    for (int b = 0; b < k2ResBufs; ++b) mbar_init(res_bar(b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // per-channel epilogue constants -> smem (read back as broadcast LDS; global loads here stalled the epilogue)
@@ -671,11 +673,25 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const bool leader = (warp == 2 && lane == 0);
     const bool has_res = p.residual != nullptr;
     uint32_t cc = 0;
-    if (leader && has_res && cluster_id < total_tiles) {
-      mbar_expect_tx(res_bar(0), kEpiBytes);
-      tma_load_2d(smem_base + Plan::kResOffset, &tmap_res, res_bar(0), (cluster_id % n_tiles) * p.bn_box,
-                  (cluster_id / n_tiles) * (2 * kBM) + (int)rank * kBM);
-    }
+    // residual chunks are prefetched k2ResBufs-1 epilogue steps ahead (a chunk = 128 rows x 64 columns, in the order
+    // the epilogue consumes them); `pf_*` is the prefetch cursor of the leader thread
+    int pf_tile = cluster_id, pf_c = 0;
+    uint32_t pf_cc = 0;
+    auto prefetch_one = [&]() {
+      if (pf_tile >= total_tiles) return;
+      const int pn0 = (pf_tile % n_tiles) * p.bn_box;
+      int pcols = p.N - pn0;
+      if (pcols > p.bn_box) pcols = p.bn_box;
+      const uint32_t b = pf_cc % k2ResBufs;
+      mbar_expect_tx(res_bar(b), kEpiBytes);
+      tma_load_2d(smem_base + Plan::kResOffset + b * kEpiBytes, &tmap_res, res_bar(b), pn0 + pf_c,
+                  (pf_tile / n_tiles) * (2 * kBM) + (int)rank * kBM);
+      ++pf_cc;
+      pf_c += kEpiCols;
+      if (pf_c >= pcols) { pf_c = 0; pf_tile += num_clusters; }
+    };
+    if (leader && has_res)
+      for (int i = 0; i < k2ResBufs - 1; ++i) prefetch_one();
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m0 = (tile / n_tiles) * (2 * kBM) + (int)rank * kBM, n0 = (tile % n_tiles) * p.bn_box;
       int n_cols = p.N - n0;
@@ -685,12 +701,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
       for (int c = 0; c < n_cols; c += kEpiCols, ++cc) {
         const uint32_t buf = cc & 1u;
+        const uint32_t rbuf = cc % k2ResBufs;
         uint8_t* out_st = smem_gen + Plan::kOutOffset + buf * kEpiBytes;
-        const uint8_t* res_st = smem_gen + Plan::kResOffset + buf * kEpiBytes;
+        const uint8_t* res_st = smem_gen + Plan::kResOffset + rbuf * kEpiBytes;
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + (uint32_t)(c + half * 32), v);
         tmem_ld_wait();
-        if (has_res) mbar_wait(res_bar(buf), (cc >> 1) & 1u);
+        if (has_res) mbar_wait(res_bar(rbuf), (cc / k2ResBufs) & 1u);
         const int n = n0 + c + half * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -734,15 +751,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (leader) {
           tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n0 + c, m0 + p.out_row_off);
           tma_store_commit();
-          if (has_res) {
-            int nt = tile, nc = c + kEpiCols;
-            if (nc >= n_cols) { nt = tile + num_clusters; nc = 0; }
-            if (nt < total_tiles) {
-              mbar_expect_tx(res_bar(buf ^ 1u), kEpiBytes);
-              tma_load_2d(smem_base + Plan::kResOffset + (buf ^ 1u) * kEpiBytes, &tmap_res, res_bar(buf ^ 1u),
-                          (nt % n_tiles) * p.bn_box + nc, (nt / n_tiles) * (2 * kBM) + (int)rank * kBM);
-            }
-          }
+          // the buffer of chunk cc-1 was fully read before the barrier above: refill it with chunk cc + k2ResBufs - 1
+          if (has_res) prefetch_one();
         }
       }
       tc_fence_before();
@@ -776,7 +786,8 @@ constexpr int kC2BBytes = 9 * 64 * 64;                   // 36 KB: nine taps x [
 constexpr int kC2AccStages = 4;
 constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + 256 + 1024;
 
-static __global__ void __launch_bounds__(kThreads, 1)
+constexpr int kC2Threads = kThreads + 32;        // + a second MMA-issuing warp (small MMAs are issue-latency bound)
+static __global__ void __launch_bounds__(kC2Threads, 1)
 conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [128 x 32] SW64*/,
                   const __grid_constant__ CUtensorMap tmap_b /*[64, 288] box [64 x 32] SW64*/, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -822,14 +833,19 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
         if (++s == kC2Stages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
+    // two issuing warps take alternate tiles: one thread sustains only ~1 tcgen05.mma per 80 cycles, and these
+    // 128x64x16 MMAs need 32 cycles of tensor pipe each
     if (lane == 0) {
       mbar_wait(b_bar, 0);
       const uint32_t idesc = make_idesc(kBM, 64);
       const uint64_t b_base = make_smem_desc<64>(b_smem);
-      int s = 0; uint32_t ph = 0;
-      int as = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int me = warp == 1 ? 0 : 1;
+      int li = 0;                                           // local tile index of this CTA
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+        if ((li & 1) != me) continue;
+        const int s = li % kC2Stages, as = li % kC2AccStages;
+        const uint32_t ph = (uint32_t)(li / kC2Stages) & 1u, aph = (uint32_t)(li / kC2AccStages) & 1u;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -845,11 +861,9 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
         }
         umma_commit(empty_bar(s));
         umma_commit(tfull_bar(as));
-        if (++s == kC2Stages) { s = 0; ph ^= 1u; }
-        if (++as == kC2AccStages) { as = 0; aph ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     const int quad = warp & 3;
     int as = 0; uint32_t aph = 0;
     // per-channel BN constants (64 channels) in registers-by-load: read once

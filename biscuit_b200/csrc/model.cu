@@ -319,7 +319,7 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
   if (grid > ctx->num_sms) grid = ctx->num_sms;
   if (blk_k == 32 && m->conv2_is && gp.conv_mode && gp.N == 64 && gp.K == 288 && 2 * gp.in_w + 2 + 128 <= kC2WinRows) {
     int g2 = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
-    conv3x3_is_kernel<<<g2, kThreads, kC2Smem, ctx->stream>>>(ta, tb, gp);
+    conv3x3_is_kernel<<<g2, kC2Threads, kC2Smem, ctx->stream>>>(ta, tb, gp);
   } else if (blk_k == 32) {
     gemm_tcgen05_kernel<32, false><<<grid, kThreads, SmemPlan<32, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
