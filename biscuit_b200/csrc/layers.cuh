@@ -271,10 +271,10 @@ depthwise3x3_smem_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W
     while (!ok) {
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, %2;\n\t"
           "selp.u32 %0, 1, 0, p;\n\t}"
           : "=r"(ok)
-          : "r"(bar)
+          : "r"(bar), "r"(0x989680u)
           : "memory");
     }
   }

@@ -17,6 +17,7 @@
 #include "layers.cuh"
 #include "head_sm100.cuh"
 #include "dw_sm100.cuh"
+#include "sepconv_sm100.cuh"
 
 using bq::bf16;
 using bq::GemmParams;
@@ -184,7 +185,7 @@ int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int 
 // ------------------------------------------------------------------------------------------------
 // execution plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP };
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED };
 
 struct Op {
   OpKind kind;
@@ -198,6 +199,7 @@ struct Op {
   int relu_in = 0, pad_top = 0, pad_left = 0;
   const float* dw = nullptr;
   const bf16* bdiag = nullptr;
+  bq::sepf::SepParams sp;     // OP_SEPFUSED
   // gemm
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
@@ -222,6 +224,7 @@ struct bq_model {
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
+  bool sep_fused = false;                      // experiment: fused depthwise->pointwise kernel for the 728->728 layers (BQ_SEPCONV=fused)
   bool conv2_is = true;                        // input-stationary block1_conv2 (BQ_CONV2=taps selects the per-tap reload kernel)
   int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
   int max_batch = 0;
@@ -448,6 +451,30 @@ int build_plan(bq_model* m) {
     m->plan.push_back(op);
     return BQ_OK;
   };
+  // one SeparableConv2D (+BN, optional ReLU / residual): fused kernel for 728->728, otherwise depthwise + GEMM
+  auto add_sep = [&](const bf16* in, bf16* dw_tmp, int h, int cin, int relu_in, const SepWeights& sw, bf16* out, int relu_out,
+                     const bf16* resid, int stage, const char* tag) -> int {
+    if (m->sep_fused && cin == 728 && sw.pw.cout == 728 && 2 * (h + 1) + 130 <= bq::sepf::kPatchRows) {
+      Op op; op.kind = OP_SEPFUSED; op.stage = stage;
+      if (tag) op.tag = tag;
+      op.in = in; op.out = out; op.in2 = resid; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = 728;
+      op.rows_per_tile = h * h;
+      op.sp.M = h * h * B; op.sp.H = h; op.sp.W = h; op.sp.C = cin; op.sp.relu_in = relu_in; op.sp.relu_out = relu_out;
+      op.sp.has_res = resid != nullptr;
+      op.sp.dw = (const float*)sw.dw.p; op.sp.scale = (const float*)sw.pw.scale.p; op.sp.shift = (const float*)sw.pw.shift.p;
+      const uint64_t rows = (uint64_t)h * h * B;
+      int r;
+      if ((r = make_tmap(ctx, &op.ta, in, rows, 728, 728, bq::sepf::kPatchRows, 64))) return r;
+      if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, 728, 728, 728, 128, 64))) return r;
+      if ((r = make_tmap(ctx, &op.tc, out, rows, 728, 728, 128, 64))) return r;
+      op.tr = op.tc;
+      if (resid && (r = make_tmap(ctx, &op.tr, resid, rows, 728, 728, 128, 64))) return r;
+      m->plan.push_back(op);
+      return BQ_OK;
+    }
+    add_dw(in, dw_tmp, h, cin, relu_in, sw, stage);
+    return add_gemm(dw_tmp, h * h, sw.pw, out, relu_out, resid, stage, tag, h, sw.pw.cout);
+  };
   // entry-style block with a strided 1x1 residual branch and a max-pool (blocks 2,3,4,13)
   auto res_block = [&](int b, int cout1, int cout2, int relu_first, int stage) -> int {
     int t[4]; others(X, t);
@@ -458,10 +485,8 @@ int build_plan(bq_model* m) {
     { Op op; op.kind = OP_SUBSAMPLE; op.stage = stage; op.in = A.p(X); op.out = A.p(t[0]); op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = C; m->plan.push_back(op); }
     int r;
     if ((r = add_gemm(A.p(t[0]), Ho * Ho, rw, A.p(t[1]), 0, nullptr, stage, nullptr, Ho, cout2))) return r;   // res -> t1
-    add_dw(A.p(X), A.p(t[0]), H, C, relu_first, s1w, stage);
-    if ((r = add_gemm(A.p(t[0]), H * H, s1w.pw, A.p(t[2]), 1, nullptr, stage, nullptr, H, cout1))) return r;
-    add_dw(A.p(t[2]), A.p(t[0]), H, cout1, 0, s2w, stage);
-    if ((r = add_gemm(A.p(t[0]), H * H, s2w.pw, A.p(t[3]), 0, nullptr, stage, nullptr, H, cout2))) return r;
+    if ((r = add_sep(A.p(X), A.p(t[0]), H, C, relu_first, s1w, A.p(t[2]), 1, nullptr, stage, nullptr))) return r;
+    if ((r = add_sep(A.p(t[2]), A.p(t[0]), H, cout1, 0, s2w, A.p(t[3]), 0, nullptr, stage, nullptr))) return r;
     { Op op; op.kind = OP_POOLADD; op.stage = stage; op.in = A.p(t[3]); op.in2 = A.p(t[1]); op.out = A.p(X);
       op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = cout2; op.Cout = cout2; op.pad_top = same_pad_before(H); op.pad_left = same_pad_before(H);
       op.tag = "block" + std::to_string(b); m->plan.push_back(op); }
@@ -474,13 +499,11 @@ int build_plan(bq_model* m) {
     int t[4]; others(X, t);
     const std::string pre = "block" + std::to_string(b) + "_sepconv";
     const SepWeights &w1 = *m->sep.at(pre + "1"), &w2 = *m->sep.at(pre + "2"), &w3 = *m->sep.at(pre + "3");
-    add_dw(A.p(X), A.p(t[0]), H, C, 1, w1, 3);
-    if ((rc = add_gemm(A.p(t[0]), H * H, w1.pw, A.p(t[1]), 1, nullptr, 3, nullptr, H, C))) return rc;
-    add_dw(A.p(t[1]), A.p(t[0]), H, C, 0, w2, 3);
-    if ((rc = add_gemm(A.p(t[0]), H * H, w2.pw, A.p(t[1]), 1, nullptr, 3, nullptr, H, C))) return rc;
-    add_dw(A.p(t[1]), A.p(t[0]), H, C, 0, w3, 3);
+    // (the unfused path ping-pongs t0 <-> t1; the fused kernel must not write its own input, so it uses t1 -> t3 -> t2)
     const std::string tag = "block" + std::to_string(b);
-    if ((rc = add_gemm(A.p(t[0]), H * H, w3.pw, A.p(t[2]), 0, A.p(X), 3, tag.c_str(), H, C))) return rc;
+    if ((rc = add_sep(A.p(X), A.p(t[0]), H, C, 1, w1, A.p(t[1]), 1, nullptr, 3, nullptr))) return rc;
+    if ((rc = add_sep(A.p(t[1]), A.p(t[0]), H, C, 0, w2, A.p(t[3]), 1, nullptr, 3, nullptr))) return rc;
+    if ((rc = add_sep(A.p(t[3]), A.p(t[0]), H, C, 0, w3, A.p(t[2]), 0, A.p(X), 3, tag.c_str()))) return rc;
     X = t[2];
   }
   // ---- exit flow
@@ -567,6 +590,16 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.Ho * op.Wo * op.C);
       bq::subsample2_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
           op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C);
+      break;
+    }
+    case OP_SEPFUSED: {
+      bq::sepf::SepParams sp = op.sp;
+      sp.M = op.rows_per_tile * nb;
+      const int items = ((sp.M + 127) / 128) * 2;
+      const int grid = items < ctx->num_sms ? items : ctx->num_sms;
+      const double px_n = (double)sp.M;
+      KScope ks(m, BQ_K_SEP_FUSED, 2.0 * px_n * sp.C * (sp.C + 9.0), act * px_n * sp.C * (sp.has_res ? 3.0 : 2.0));
+      bq::sepf::sepconv_fused_kernel<<<grid, bq::sepf::kThreads, bq::sepf::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sp);
       break;
     }
     case OP_GAP: {
@@ -788,6 +821,9 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
   cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::head::HeadSmem::kTotal);
+  const char* sf = getenv("BQ_SEPCONV");
+  m->sep_fused = sf && strcmp(sf, "fused") == 0;
+  cudaFuncSetAttribute(bq::sepf::sepconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepf::kSmem);
   const char* c2 = getenv("BQ_CONV2");
   m->conv2_is = !(c2 && strcmp(c2, "taps") == 0);
   cudaFuncSetAttribute(bq::sm100::conv3x3_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sm100::kC2Smem);
