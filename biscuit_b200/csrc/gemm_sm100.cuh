@@ -167,6 +167,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk store have finished reading their smem source (double-buffered staging)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -504,10 +506,11 @@ struct SmemPlan2 {
   static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (half of the N tile)
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutOffset = k2Stages * kStageBytes;
-  static constexpr int kResOffset = kOutOffset + 2 * kEpiBytes;
-  static constexpr int kScaleOffset = kResOffset + k2ResBufs * kEpiBytes;   // float scale[k2MaxN], shift[k2MaxN]
+  static constexpr int kScaleOffset = kOutOffset + 2 * kEpiBytes;           // float scale[k2MaxN], shift[k2MaxN]
   static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static constexpr int kResOffset = kBarOffset + 1024;                      // residual staging LAST: only requested when used
+  static constexpr int kTotalNoRes = kResOffset + 1024;                     // 165 KB: leaves room for a co-resident depthwise block
+  static constexpr int kTotal = kResOffset + k2ResBufs * kEpiBytes + 1024;  // + 1 KB slack for the 1024 B alignment
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {

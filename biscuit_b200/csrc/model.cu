@@ -18,6 +18,7 @@
 #include "head_sm100.cuh"
 #include "dw_sm100.cuh"
 #include "sepconv_sm100.cuh"
+#include "sepconv2d_sm100.cuh"
 
 using bq::bf16;
 using bq::GemmParams;
@@ -185,7 +186,7 @@ int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int 
 // ------------------------------------------------------------------------------------------------
 // execution plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED };
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED, OP_SEP2D };
 
 struct Op {
   OpKind kind;
@@ -200,6 +201,7 @@ struct Op {
   const float* dw = nullptr;
   const bf16* bdiag = nullptr;
   bq::sepf::SepParams sp;     // OP_SEPFUSED
+  bq::sep2d::Sep2dParams s2;  // OP_SEP2D
   // gemm
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
@@ -224,6 +226,8 @@ struct bq_model {
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
+  bool sep2d = true;                           // fused 2-D-patch sepconv for the K <= 256, N <= 256 entry-flow layers (BQ_SEP2D=off)
+  bool dw_cc32 = false;                        // 32-channel depthwise blocks (more blocks per SM) for C % 64 == 0 layers
   bool sep_fused = false;                      // experiment: fused depthwise->pointwise kernel for the 728->728 layers (BQ_SEPCONV=fused)
   bool conv2_is = true;                        // input-stationary block1_conv2 (BQ_CONV2=taps selects the per-tap reload kernel)
   int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
@@ -328,7 +332,8 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
   } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
     const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
     int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
-    gemm_tcgen05_2cta_kernel<<<2 * clusters, k2Threads, SmemPlan2::kTotal, ctx->stream>>>(ta, *tb_half, tc, tr, gp);
+    gemm_tcgen05_2cta_kernel<<<2 * clusters, k2Threads, gp.residual ? SmemPlan2::kTotal : SmemPlan2::kTotalNoRes, ctx->stream>>>(
+        ta, *tb_half, tc, tr, gp);
   } else if (m->gemm_direct_epi) {
     gemm_tcgen05_kernel<64, false><<<grid, kThreads, SmemPlan<64, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else {
@@ -431,7 +436,7 @@ int build_plan(bq_model* m) {
   auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
     Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
     op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
-    const int CC = (c % 64 == 0) ? 64 : 56;
+    const int CC = (c % 64 != 0) ? 56 : (m->dw_cc32 ? 32 : 64);
     int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::kDwHalo, bq::kDwHalo, CC);
     if (r && !dw_rc) dw_rc = r;
     r = make_tmap_nhwc(ctx, &op.tb, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kHalo, bq::dwtc::kHalo, 64, true);
@@ -469,6 +474,20 @@ int build_plan(bq_model* m) {
       if ((r = make_tmap(ctx, &op.tc, out, rows, 728, 728, 128, 64))) return r;
       op.tr = op.tc;
       if (resid && (r = make_tmap(ctx, &op.tr, resid, rows, 728, 728, 128, 64))) return r;
+      m->plan.push_back(op);
+      return BQ_OK;
+    }
+    if (m->sep2d && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
+      Op op; op.kind = OP_SEP2D; op.stage = stage;
+      if (tag) op.tag = tag;
+      op.in = in; op.out = out; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = sw.pw.cout;
+      op.s2.n_img = B; op.s2.H = h; op.s2.W = h; op.s2.K = cin; op.s2.N = sw.pw.cout;
+      op.s2.relu_in = relu_in; op.s2.relu_out = relu_out;
+      op.s2.dw = (const float*)sw.dw.p; op.s2.scale = (const float*)sw.pw.scale.p; op.s2.shift = (const float*)sw.pw.shift.p;
+      int r;
+      if ((r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)cin, bq::sep2d::kHH, bq::sep2d::kHW, 64, false))) return r;
+      if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, (uint64_t)sw.pw.cout, (uint64_t)cin, (uint64_t)cin, (uint32_t)sw.pw.cout, 64))) return r;
+      if ((r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)sw.pw.cout, bq::sep2d::kPH, bq::sep2d::kPW, 64, true))) return r;
       m->plan.push_back(op);
       return BQ_OK;
     }
@@ -570,7 +589,7 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
         bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
             op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
       } else {
-        const int CC = (op.C % 64 == 0) ? 64 : 56;              // 728 = 13 x 56
+        const int CC = (op.C % 64 != 0) ? 56 : (m->dw_cc32 ? 32 : 64);   // 728 = 13 x 56
         const int tiles = (op.H + bq::kDwTile - 1) / bq::kDwTile;
         dim3 grid((op.C + CC - 1) / CC, tiles * tiles, nb);
         const int threads = (CC / 4) * bq::kDwTile;
@@ -600,6 +619,20 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       const double px_n = (double)sp.M;
       KScope ks(m, BQ_K_SEP_FUSED, 2.0 * px_n * sp.C * (sp.C + 9.0), act * px_n * sp.C * (sp.has_res ? 3.0 : 2.0));
       bq::sepf::sepconv_fused_kernel<<<grid, bq::sepf::kThreads, bq::sepf::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sp);
+      break;
+    }
+    case OP_SEP2D: {
+      bq::sep2d::Sep2dParams s2 = op.s2;
+      s2.n_img = nb;
+      const int items = nb * ((op.H + bq::sep2d::kPH - 1) / bq::sep2d::kPH) * ((op.W + bq::sep2d::kPW - 1) / bq::sep2d::kPW);
+      const int grid = items < ctx->num_sms ? items : ctx->num_sms;
+      const double px_n = (double)nb * op.H * op.W;
+      KScope ks(m, BQ_K_SEP_FUSED, 2.0 * px_n * s2.K * (s2.N + 9.0), act * px_n * (s2.K + s2.N));
+      const int smem2d = bq::sep2d::smem_bytes(s2.N);
+      if (s2.relu_in)
+        bq::sep2d::sepconv2d_fused_kernel<true><<<grid, bq::sep2d::kThreads, smem2d, ctx->stream>>>(op.ta, op.tb, op.tc, s2);
+      else
+        bq::sep2d::sepconv2d_fused_kernel<false><<<grid, bq::sep2d::kThreads, smem2d, ctx->stream>>>(op.ta, op.tb, op.tc, s2);
       break;
     }
     case OP_GAP: {
@@ -821,6 +854,12 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
   cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::head::HeadSmem::kTotal);
+  const char* s2d = getenv("BQ_SEP2D");
+  m->sep2d = !(s2d && strcmp(s2d, "off") == 0);
+  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
+  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
+  const char* cc32 = getenv("BQ_DW_CC");
+  m->dw_cc32 = cc32 && atoi(cc32) == 32;
   const char* sf = getenv("BQ_SEPCONV");
   m->sep_fused = sf && strcmp(sf, "fused") == 0;
   cudaFuncSetAttribute(bq::sepf::sepconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepf::kSmem);

@@ -1,0 +1,291 @@
+// Fused SeparableConv2D for the entry-flow layers with K <= 256 and N <= 256 (block2 / block3 sepconvs on the 147^2 and
+// 74^2 maps -- the layers that are HBM-bound when the depthwise result makes a round trip through memory):
+//
+//     out[8x16 px, N] = epilogue( depthwise3x3(relu?(x))[8x16 px, K] @ Wpw[N, K]^T )
+//
+// A work item is an 8 x 16 pixel patch of one image (= the 128 rows of a UMMA M tile).  Per 64-channel k-block:
+//   warp 0      one 4-D TMA load of the (8+2) x (16+2) x 64 halo patch (zero fill outside the image = 'same' padding) and
+//               one TMA load of the [N x 64] pointwise-weight k-block;
+//   warps 6-13  depthwise producers: thread = (4 channels, one patch column), vertical 3x3 register window walking down
+//               the 8 rows (3 LDS.64 + 18 FFMA2 per 4 outputs, weights in registers) -> bf16 -> the 128B-swizzled A stage;
+//   warp 1      tcgen05.mma 128 x N x 16 (x4 per k-block), accumulators double-buffered in TMEM;
+//   warps 2-5   epilogue: tcgen05.ld -> BN scale/shift -> ReLU -> bf16 -> swizzled staging -> 4-D TMA store (image border
+//               clipped by the TMA unit).
+// The depthwise output never touches L2/HBM (saves one tensor write + one tensor read per layer) and its CUDA-core work
+// runs under the TMA / tensor-core work of the same kernel.
+#pragma once
+
+#include "gemm_sm100.cuh"
+
+namespace bq {
+namespace sep2d {
+
+using namespace sm100;
+
+constexpr int kPH = 8, kPW = 16;                               // output patch (rows x cols) = 128 pixels
+constexpr int kHH = kPH + 2, kHW = kPW + 2;                    // halo patch 10 x 18
+constexpr int kPatchBytes = 23 * 1024;                         // 10*18*128 = 23,040 B, padded to a multiple of 1024
+constexpr int kABytes = 128 * 128;
+constexpr int kOutBytes = 128 * 128;
+constexpr int kMaxPStages = 5, kAStages = 2, kBStages = 2;
+constexpr int kOffPatch = 0;
+// runtime layout (all offsets multiples of 1024): [patch x P][A x 2][B x 2 (N*128 B each)][out x 2][scale/shift][barriers]
+// P = 4 halo-patch stages for N = 256, 5 for N <= 128: the kernel is HBM-latency bound, so every spare KB is patch in flight
+__host__ __device__ inline int patch_stages(int N) { return N > 128 ? 4 : 5; }
+__host__ __device__ inline int off_a(int N) { return patch_stages(N) * kPatchBytes; }
+__host__ __device__ inline int off_b(int N) { return off_a(N) + kAStages * kABytes; }
+__host__ __device__ inline int off_out(int N) { return off_b(N) + kBStages * N * 128; }
+__host__ __device__ inline int off_scale(int N) { return off_out(N) + 2 * kOutBytes; }
+__host__ __device__ inline int off_bar(int N) { return off_scale(N) + 2 * 256 * 4; }
+__host__ __device__ inline int smem_bytes(int N) { return off_bar(N) + 512 + 1024; }
+constexpr int kThreads = 576;                                 // warp 0 TMA, 1 MMA, 2-9 epilogue (8), 10-17 producers (8)
+constexpr int kProducerWarps = 8;
+
+struct Sep2dParams {
+  int n_img, H, W;          // images in this launch, map size
+  int K, N;                 // input / output channels (K % 64 == 0, K <= 256; N % 16 == 0, N <= 256)
+  int relu_in, relu_out;
+  const float* dw;          // [9][K]
+  const float* scale;       // [N]
+  const float* shift;
+};
+
+template <bool RELU_IN>
+__global__ void __launch_bounds__(kThreads, 1)
+sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H, n] box [64, 18, 10, 1], no swizzle*/,
+                       const __grid_constant__ CUtensorMap tmap_w /*2-D [N, K] box [64 x N], SW128*/,
+                       const __grid_constant__ CUtensorMap tmap_out /*4-D [N, W, H, n] box [64, 16, 8, 1], SW128*/,
+                       const Sep2dParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int kPStages = patch_stages(p.N);
+  const int kOffA = off_a(p.N), kOffB = off_b(p.N), kOffOut = off_out(p.N), kOffScale = off_scale(p.N), kOffBar = off_bar(p.N);
+  const int kBBytes = p.N * 128;
+  const uint32_t bar0 = smem_base + kOffBar;
+  auto patch_full = [&](int s) { return bar0 + 8u * s; };                       // [5]
+  auto patch_empty = [&](int s) { return bar0 + 8u * (5 + s); };                // [5]
+  auto a_full = [&](int s) { return bar0 + 8u * (10 + s); };                    // [2]
+  auto a_empty = [&](int s) { return bar0 + 8u * (12 + s); };                   // [2]
+  auto b_full = [&](int s) { return bar0 + 8u * (14 + s); };                    // [2]
+  auto b_empty = [&](int s) { return bar0 + 8u * (16 + s); };                   // [2]
+  auto acc_full = [&](int s) { return bar0 + 8u * (18 + s); };                  // [2]
+  auto acc_empty = [&](int s) { return bar0 + 8u * (20 + s); };                 // [2]
+  const uint32_t tmem_slot = bar0 + 8u * 22;
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * 22);
+  float* s_scale = (float*)(smem_gen + kOffScale);
+  float* s_shift = s_scale + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px_tiles = (p.W + kPW - 1) / kPW, py_tiles = (p.H + kPH - 1) / kPH;
+  const int per_img = px_tiles * py_tiles;
+  const int n_items = p.n_img * per_img;
+  const int num_kb = p.K / 64;
+  const uint32_t b_bytes = (uint32_t)p.N * 128u;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < kPStages; ++s) { mbar_init(patch_full(s), 1); mbar_init(patch_empty(s), kProducerWarps); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), kProducerWarps); mbar_init(a_empty(s), 1);
+      mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1);
+      mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) { s_scale[i] = __ldg(p.scale + i); s_shift[i] = __ldg(p.shift + i); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA: halo patch + weight k-block =====================
+    if (lane == 0) {
+      int ps = 0; uint32_t pph = 0;
+      int bs = 0; uint32_t bph = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int img = it / per_img, t = it - img * per_img;
+        const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(patch_empty(ps), pph ^ 1u);
+          mbar_expect_tx(patch_full(ps), (uint32_t)(kHH * kHW * 128));
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(smem_base + kOffPatch + ps * kPatchBytes), "l"((uint64_t)&tmap_x), "r"(patch_full(ps)), "r"(kb * 64),
+                "r"(x0 - 1), "r"(y0 - 1), "r"(img)
+              : "memory");
+          if (++ps == kPStages) { ps = 0; pph ^= 1u; }
+          mbar_wait(b_empty(bs), bph ^ 1u);
+          mbar_expect_tx(b_full(bs), b_bytes);
+          tma_load_2d(smem_base + kOffB + bs * kBBytes, &tmap_w, b_full(bs), kb * 64, 0);
+          if (++bs == kBStages) { bs = 0; bph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.N);
+      int as = 0; uint32_t aph = 0;                // A / B rings advance together (one step per k-block)
+      int cs = 0; uint32_t cph = 0;                // accumulator stage per item
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        mbar_wait(acc_empty(cs), cph ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(cs * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(a_full(as), aph);
+          mbar_wait(b_full(as), aph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc<128>(smem_base + kOffA + as * kABytes);
+          const uint64_t db = make_smem_desc<128>(smem_base + kOffB + as * kBBytes);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(a_empty(as));
+          umma_commit(b_empty(as));
+          if (kb == num_kb - 1) umma_commit(acc_full(cs));
+          if (++as == 2) { as = 0; aph ^= 1u; }
+        }
+        if (++cs == 2) { cs = 0; cph ^= 1u; }
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== epilogue: 8 warps = (TMEM lane quadrant, 32-column half of each 64-column chunk) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    int cs = 0; uint32_t cph = 0, cc = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int img = it / per_img, t = it - img * per_img;
+      const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
+      mbar_wait(acc_full(cs), cph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * 256);
+      for (int c = 0; c < p.N; c += 64, ++cc) {
+        const uint32_t buf = cc & 1u;
+        uint8_t* st = smem_gen + kOffOut + buf * kOutBytes;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(c + half * 32), v);
+        tmem_ld_wait();
+        if (c + 64 >= p.N) {                                    // accumulators fully read -> next item may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(cs));
+        }
+        if (leader) tma_store_wait_read1();                     // the store that last used THIS staging buffer has drained
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = c + half * 32 + g * 8;
+          float f[8];
+          if (n < p.N) {
+            const float4 s0 = *(const float4*)(s_scale + n), s1 = *(const float4*)(s_scale + n + 4);
+            const float4 h0 = *(const float4*)(s_shift + n), h1 = *(const float4*)(s_shift + n + 4);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
+              if (p.relu_out) f[j] = fmaxf(f[j], 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          }
+          uint4 o;
+          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          const int chunk16 = half * 4 + g;
+          *(uint4*)(st + (size_t)row * 128 + ((chunk16 ^ (row & 7)) << 4)) = o;
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"((uint64_t)&tmap_out), "r"(smem_base + kOffOut + buf * kOutBytes), "r"(c), "r"(x0), "r"(y0), "r"(img)
+                       : "memory");
+          tma_store_commit();
+        }
+      }
+      if (++cs == 2) { cs = 0; cph ^= 1u; }
+    }
+    if (leader) tma_store_wait_all();
+  } else {
+    // ===================== depthwise producers: thread = (4 channels, patch column), walks down 8 rows =====================
+    const int ptid = threadIdx.x - 320;                         // 0..255
+    const int c4 = ptid & 15, px = ptid >> 4;                   // channel group, column 0..15
+    int ps = 0; uint32_t pph = 0;
+    int as = 0; uint32_t aph = 0;
+    auto load3 = [&](const uint8_t* rowp, float2 (&d)[3][2]) {  // pixels px-1, px, px+1 of one halo row
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        uint2 raw = *(const uint2*)(rowp + (size_t)k * 128);
+        if (RELU_IN) {                                            // ReLU on the packed bf16 pairs (2 instead of 4 instructions)
+          const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+          __nv_bfloat162* hb = (__nv_bfloat162*)&raw;
+          hb[0] = __hmax2(hb[0], z2);
+          hb[1] = __hmax2(hb[1], z2);
+        }
+        d[k][0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
+        d[k][1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+      }
+    };
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int c = kb * 64 + c4 * 4;
+        float2 w[9][2];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 wv = __ldg((const float4*)(p.dw + (size_t)t * p.K + c));
+          w[t][0] = make_float2(wv.x, wv.y);
+          w[t][1] = make_float2(wv.z, wv.w);
+        }
+        mbar_wait(patch_full(ps), pph);
+        mbar_wait(a_empty(as), aph ^ 1u);
+        const uint8_t* col = smem_gen + kOffPatch + ps * kPatchBytes + (size_t)px * 128 + c4 * 8;   // halo (row 0, col px)
+        uint8_t* a_dst = smem_gen + kOffA + as * kABytes;
+        float2 ra[3][2], rb[3][2], rc[3][2];
+        load3(col, ra);
+        load3(col + (size_t)kHW * 128, rb);
+        auto step = [&](const float2 (&r0)[3][2], const float2 (&r1)[3][2], float2 (&r2)[3][2], int py) {
+          load3(col + (size_t)(py + 2) * kHW * 128, r2);
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r0[kx][0], w[kx][0], a0); a1 = __ffma2_rn(r0[kx][1], w[kx][1], a1); }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r1[kx][0], w[3 + kx][0], a0); a1 = __ffma2_rn(r1[kx][1], w[3 + kx][1], a1); }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r2[kx][0], w[6 + kx][0], a0); a1 = __ffma2_rn(r2[kx][1], w[6 + kx][1], a1); }
+          const int r = py * kPW + px;                           // A row of this output pixel
+          uint2 o;
+          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+          ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
+          ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
+          *(uint2*)(a_dst + (size_t)r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8) = o;
+        };
+        step(ra, rb, rc, 0); step(rb, rc, ra, 1); step(rc, ra, rb, 2);
+        step(ra, rb, rc, 3); step(rb, rc, ra, 4); step(rc, ra, rb, 5);
+        step(ra, rb, rc, 6); step(rb, rc, ra, 7);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(a_full(as)); mbar_arrive(patch_empty(ps)); }
+        if (++ps == kPStages) { ps = 0; pph ^= 1u; }
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace sep2d
+}  // namespace bq

@@ -207,8 +207,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*[M, C] box [64
         // residual may land in the OTHER buffer, the store of chunk cc-1 must have finished reading it -- it has had the
         // whole previous chunk to drain, so the leader checks that first and prefetches one chunk ahead.
         if (leader) {
-          tma_store_wait_read0();
-          prefetch_res();                                       // chunk cc+1 (no-op without a residual)
+          tma_store_wait_read1();                               // store of chunk cc-2 (this buffer) has drained; cc-1 may be in flight
+          if (p.has_res) { tma_store_wait_read0(); prefetch_res(); }   // the residual of chunk cc+1 lands in chunk cc-1's buffer
         }
         if (p.has_res) {
           mbar_wait(res_bar(buf), (cc >> 1) & 1u);

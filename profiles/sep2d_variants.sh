@@ -1,0 +1,8 @@
+#!/bin/bash
+# Developer helper (run under gpurun): fused 2-D-patch sepconv for the entry flow vs separate depthwise + GEMM.
+timeout 600 python -m pytest tests/test_model_gpu.py -x -q -m gpu 2>&1 | tail -4
+for v in "on" "off"; do
+  echo "=== BQ_SEP2D=$v"
+  BQ_SEP2D=$v timeout 300 python bench.py --tiles 4096 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('tiles/s %.0f'%d['value']); [print('  %-16s %8.2f ms  %7.1f TF  %7.0f GB/s  x%d'%(k,v['ms'],v['tflops'],v['gbs'],v['launches'])) for k,v in d['kernels'].items() if v['ms']>2]"
+done
