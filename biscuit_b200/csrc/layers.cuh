@@ -337,27 +337,38 @@ maxpool_add_kernel(const bf16* __restrict__ in, const bf16* __restrict__ res, bf
     pix /= Wo;
     const int yo = (int)(pix % Ho);
     const int img = (int)(pix / Ho);
-    float m[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    // Window taps that fall into the padding are clamped onto the nearest valid pixel: a duplicate never changes
+    // a maximum, so all nine 16-byte loads are unconditional and in flight together; the max itself is exact in bf16.
     const bf16* base = in + ((int64_t)img * H * W) * C + c8 * 8;
+    uint4 v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yy = yo * 2 + ky - pad_top;
-      if (yy < 0 || yy >= H) continue;
+      const int yy = min(max(yo * 2 + ky - pad_top, 0), H - 1);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int xx = xo * 2 + kx - pad_left;
-        if (xx < 0 || xx >= W) continue;
-        float f[8];
-        bf16x8_to_float(__ldg((const uint4*)(base + ((int64_t)yy * W + xx) * C)), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        const int xx = min(max(xo * 2 + kx - pad_left, 0), W - 1);
+        v[ky * 3 + kx] = __ldg((const uint4*)(base + ((int64_t)yy * W + xx) * C));
       }
+    }
+    const uint4 rv = __ldg((const uint4*)(res + (((int64_t)img * Ho + yo) * Wo + xo) * C + c8 * 8));
+    __nv_bfloat162 mx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 a = ((const __nv_bfloat162*)&v[0])[q];
+#pragma unroll
+      for (int k = 1; k < 9; ++k) a = __hmax2(a, ((const __nv_bfloat162*)&v[k])[q]);
+      mx[q] = a;
+    }
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __bfloat1622float2(mx[q]);
+      m[2 * q] = f.x;
+      m[2 * q + 1] = f.y;
     }
     const int64_t o = (((int64_t)img * Ho + yo) * Wo + xo) * C + c8 * 8;
     float r[8];
-    bf16x8_to_float(__ldg((const uint4*)(res + o)), r);
+    bf16x8_to_float(rv, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = __fadd_rn(m[j], r[j]);
     *(uint4*)(out + o) = float_to_bf16x8(m);
