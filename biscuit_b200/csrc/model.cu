@@ -17,6 +17,7 @@
 #include "layers.cuh"
 #include "head_sm100.cuh"
 #include "dw_sm100.cuh"
+#include "dwpipe_sm100.cuh"
 #include "sepconv_sm100.cuh"
 #include "sepconv2d_sm100.cuh"
 
@@ -222,7 +223,7 @@ struct bq_model {
   bq_model_config cfg{};
   bool weights_loaded = false;
   bool use_simt = false;
-  int dw_mode = 1;                             // 1: smem + FFMA2 sliding window (default), 2: tensor-core depthwise, 0: first generation
+  int dw_mode = 3;                             // 3: persistent TMA-pipelined (default), 1: one tile per block, 2: tensor-core, 0: first generation
   bool gemm_direct_epi = false;
   bool gemm_2cta = true;
   bool head_fused = true;
@@ -588,6 +589,17 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       } else if (m->dw_mode == 0) {
         bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
             op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
+      } else if (m->dw_mode == 3) {
+        const int CC = (op.C % 64 != 0) ? 56 : 64;                        // 728 = 13 x 56
+        const int tiles = (op.H + bq::dwp::kTile - 1) / bq::dwp::kTile;
+        const int64_t items = (int64_t)nb * tiles * tiles * (op.C / CC);
+        const int grid = (int)std::min<int64_t>(items, ctx->num_sms);
+#define BQ_DWP_LAUNCH(RELU, CCV)                                                                              \
+  bq::dwp::depthwise3x3_pipe_kernel<RELU, CCV><<<grid, bq::dwp::kThreads, bq::dwp::kSmem, ctx->stream>>>(    \
+      op.ta, op.dw, op.out, nb, op.H, op.W, op.C, tiles)
+        if (CC == 56) { if (op.relu_in) BQ_DWP_LAUNCH(true, 56); else BQ_DWP_LAUNCH(false, 56); }
+        else          { if (op.relu_in) BQ_DWP_LAUNCH(true, 64); else BQ_DWP_LAUNCH(false, 64); }
+#undef BQ_DWP_LAUNCH
       } else {
         const int CC = (op.C % 64 != 0) ? 56 : (m->dw_cc32 ? 32 : 64);   // 728 = 13 x 56
         const int tiles = (op.H + bq::kDwTile - 1) / bq::kDwTile;
@@ -869,7 +881,12 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   const char* eb = getenv("BQ_ENTRY_BATCH");
   if (eb) m->entry_batch = atoi(eb);
   const char* dwv = getenv("BQ_DW");
-  m->dw_mode = dwv && strcmp(dwv, "v1") == 0 ? 0 : (dwv && strcmp(dwv, "tc") == 0 ? 2 : 1);   // experiment switches
+  // default 3 = persistent TMA-pipelined kernel; v1 / v2 / tc are the earlier generations kept as experiment switches
+  m->dw_mode = !dwv ? 3 : strcmp(dwv, "v1") == 0 ? 0 : strcmp(dwv, "v2") == 0 ? 1 : strcmp(dwv, "tc") == 0 ? 2 : 3;
+  cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
+  cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
+  cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
+  cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
   cudaFuncSetAttribute(bq::dwtc::depthwise3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwtc::kSmem);
   cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::kDwHalo * bq::kDwHalo * 64 * (int)sizeof(bf16));
