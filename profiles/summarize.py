@@ -10,7 +10,7 @@ import os
 import sys
 from collections import OrderedDict
 
-FAMILY = [("gemm_tcgen05_2cta", "gemm_pointwise"), ("conv3x3_is", "gemm_conv2"), ("mc_head_fused", "head_fused"), ("gemm_tcgen05_kernel<32", "gemm_conv2"), ("gemm_tcgen05_kernel", "gemm_pointwise"),
+FAMILY = [("sepconv2d_fused", "sepconv_fused"), ("sepconv_fused", "sepconv_fused"), ("gemm_tcgen05_2cta", "gemm_pointwise"), ("conv3x3_is", "gemm_conv2"), ("mc_head_fused", "head_fused"), ("gemm_tcgen05_kernel<32", "gemm_conv2"), ("gemm_tcgen05_kernel", "gemm_pointwise"),
           ("depthwise3x3", "depthwise"), ("maxpool_add", "maxpool_add"), ("subsample2", "subsample"), ("conv1_kernel", "conv1"),
           ("tile_stats", "tile_stats"), ("gap_kernel", "gap"), ("mc_expand", "mc_expand"), ("head_final", "head_final"),
           ("group_kahan", "threshold"), ("roc_", "threshold"), ("seg_bounds", "threshold"), ("group_apply", "threshold"),
@@ -64,12 +64,17 @@ def main(path, tag):
         out.append(f"| {f} | {a['n']} | {a['us']:.1f} | {100 * a['us'] / total:.1f} % | {a['rd'] / 1e6:.1f} | {a['wr'] / 1e6:.1f} |")
         traffic[f] = {"dram_bytes_per_launch": (a["rd"] + a["wr"]) / max(1, a["n"]), "launches": a["n"],
                       "share_of_step": a["us"] / total}
+    # per-launch list in execution order (kernel, grid-independent): lets a reader map every GEMM to its layer
+    out += ["", "## launches in execution order", "", "| # | kernel | us | DRAM read MB | DRAM write MB |", "|---|---|---|---|---|"]
+    for i, d in enumerate(seq):
+        short = d["name"].split("(")[0].replace("void ", "").replace("bq::", "")
+        out.append(f"| {i} | `{short[:60]}` | {d.get('us', 0):.1f} | {d.get('rd', 0) / 1e6:.1f} | {d.get('wr', 0) / 1e6:.1f} |")
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, f"launches_{tag}.md"), "w") as f:
         f.write("\n".join(out) + "\n")
     with open(os.path.join(here, "roofline_traffic.json"), "w") as f:
         json.dump({"source": os.path.basename(path), "tag": tag, **traffic}, f, indent=1)
-    print("\n".join(out))
+    print("\n".join(out[:24]))
 
 
 if __name__ == "__main__":
