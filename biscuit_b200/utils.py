@@ -1,11 +1,21 @@
-"""Column contract and ROC helpers -- the parts of reference biscuit/utils.py that sit on the hot
-path: `uncertainty_header / y_true_header / y_pred_header` (19-28), `rename_cols` (31-53),
-`auc_and_threshold` (467-484) and `auc` (487-504).  The ROC arithmetic runs on the GPU (bq_roc)."""
+"""Column contract, prediction-table loaders and ROC helpers -- the parts of reference biscuit/utils.py
+that sit on (or right next to) the hot path: `uncertainty_header / y_true_header / y_pred_header`
+(19-28), `rename_cols` (31-53), `df_from_cv` (190-228), `find_model / model_exists / find_cv`
+(233-311), `auc_and_threshold` (467-484) and `auc` (487-504).  The ROC arithmetic runs on the GPU
+(bq_roc); the loaders are host-side pandas I/O exactly as in the reference, so a table read from CSV
+is float64 and one read from parquet keeps its float32 columns -- the dtype the GPU path then
+computes in."""
 from __future__ import annotations
 
+import csv
 import logging
+import os
+from os.path import join
 
 import numpy as np
+import pandas as pd
+
+from .errors import ModelNotFoundError, MultipleModelsFoundError
 
 log = logging.getLogger("biscuit_b200")
 
@@ -69,3 +79,89 @@ def auc(y_true, y_pred):
     except ValueError:
         log.warning("Unable to calculate ROC")
         return np.nan
+
+
+# --- prediction-table loaders and model lookup --------------------------------
+
+def find_model(project, label, outcome, epoch=None, kfold=None):
+    """Path of the trained model `{outcome}-{label}-HP0[-kfold{k}]` inside ``project.models_dir``
+    (Slideflow prefixes every model folder with a 5-digit id and a dash, hence the ``[6:]``);
+    with ``epoch`` the saved-model sub-folder, else the parent folder.  Raises
+    ModelNotFoundError / MultipleModelsFoundError (reference utils.py:233-272)."""
+    tail = "" if kfold is None else f"-kfold{kfold}"
+    name = f"{outcome}-{label}-HP0{tail}"
+    matching = [o for o in os.listdir(project.models_dir) if o[6:] == name]
+    if len(matching) > 1:
+        raise MultipleModelsFoundError(f"Multiple matching models found matching {name}")
+    if not matching:
+        raise ModelNotFoundError(f"No matching model found matching {name}.")
+    if epoch is not None:
+        return join(project.models_dir, matching[0], f"{name}_epoch{epoch}")
+    return join(project.models_dir, matching[0])
+
+
+def model_exists(project, label, outcome, epoch=None, kfold=None):
+    """True if :func:`find_model` finds exactly one match (reference utils.py:275-292; more than
+    one match still raises, as there)."""
+    try:
+        find_model(project, label, outcome, kfold=kfold, epoch=epoch)
+        return True
+    except ModelNotFoundError:
+        return False
+
+
+def find_cv(project, label, outcome, epoch=None, k=3):
+    """Paths of the k cross-validation models of one experiment (reference utils.py:295-311)."""
+    return [find_model(project, label, outcome, epoch=epoch, kfold=_k) for _k in range(1, k + 1)]
+
+
+def read_tile_predictions(path):
+    """One Slideflow tile-prediction table: ``.csv`` (slide column forced to str, reference
+    experiment.py:980-981) or ``.parquet`` / ``.parquet.gzip`` (982-983); anything else is an
+    OSError (984-985)."""
+    ext = path.rsplit(".", 1)[-1].lower()
+    if ext == "csv":
+        return pd.read_csv(path, dtype={"slide": str})
+    if ext in ("parquet", "gzip"):
+        return pd.read_parquet(path)
+    raise OSError(f"Unrecognized prediction filetype {path}")
+
+
+def df_from_cv(project, label, outcome, epoch=None, k=3, y_true=None, y_pred=None, uncertainty=None):
+    """Tile-prediction tables of the k cross-validation folds of `label`, columns renamed to
+    y_true / y_pred / uncertainty and a ``patient`` column added from the project's slide ->
+    patient map when the file has none (reference utils.py:190-228).  CSV wins over
+    ``.parquet.gzip`` when both exist, as in the reference."""
+    dfs = []
+    folders = find_cv(project, label, epoch=epoch, k=k, outcome=outcome)
+    patients = project.dataset().patients()
+    e = "" if epoch is None else "../"
+    for folder in folders:
+        csv_path = join(folder, f"{e}tile_predictions_val_epoch1.csv")
+        parquet_path = join(folder, f"{e}tile_predictions_val_epoch1.parquet.gzip")
+        if os.path.exists(csv_path):
+            df = pd.read_csv(csv_path)
+        elif os.path.exists(parquet_path):
+            df = pd.read_parquet(parquet_path)
+        else:
+            raise OSError(f"Could not find tile predictions file at {folder}")
+        rename_cols(df, outcome, y_true=y_true, y_pred=y_pred, uncertainty=uncertainty)
+        if "patient" not in df.columns:
+            df["patient"] = df["slide"].map(patients)
+        dfs.append(df)
+    return dfs
+
+
+def slides_from_model_manifest(model_path, dataset=None):
+    """Slide names listed in a trained model's ``slide_manifest.csv`` (looked up in the model folder,
+    then its parent), optionally restricted to one dataset ('training' / 'validation').  Stands in
+    for ``sf.util.get_slides_from_model_manifest`` which reference experiment.py:1008 calls to
+    report ``n_slides``; Slideflow is an external dependency, so this follows its documented file
+    format (header row with 'slide' and 'dataset' columns)."""
+    for folder in (model_path, os.path.dirname(os.path.normpath(model_path))):
+        path = join(folder, "slide_manifest.csv")
+        if os.path.exists(path):
+            with open(path, newline="") as f:
+                rows = list(csv.DictReader(f))
+            return [r["slide"] for r in rows if dataset is None or r.get("dataset") == dataset]
+    raise OSError(f"Could not find slide manifest for model {model_path}")

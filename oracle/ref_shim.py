@@ -63,7 +63,19 @@ def load_reference():
             self.__dict__.update(kw)
 
     if "slideflow" not in sys.modules:
-        sf_util = _stub("slideflow.util", log=log, path_to_ext=lambda p: p.rsplit(".", 1)[-1])
+        def _manifest_slides(model_path, dataset=None):
+            # documented behaviour of sf.util.get_slides_from_model_manifest: slide_manifest.csv in the model
+            # folder or its parent, optional dataset filter (only the row COUNT reaches the reference's output)
+            import csv
+            for folder in (model_path, os.path.dirname(os.path.normpath(model_path))):
+                path = os.path.join(folder, "slide_manifest.csv")
+                if os.path.exists(path):
+                    with open(path, newline="") as f:
+                        return [r["slide"] for r in csv.DictReader(f) if dataset is None or r["dataset"] == dataset]
+            raise OSError(f"no slide manifest for {model_path}")
+
+        sf_util = _stub("slideflow.util", log=log, path_to_ext=lambda p: p.rsplit(".", 1)[-1],
+                        bold=lambda t: t, get_slides_from_model_manifest=_manifest_slides)
         sf_model = _stub("slideflow.model", ModelParams=_ModelParams)
         sf = _stub("slideflow", util=sf_util, model=sf_model, Project=type("Project", (), {}))
         sf.__path__ = []

@@ -73,6 +73,88 @@ def patients_map(df):
 
 
 # ----------------------------------------------------------------------------------------
+# a Slideflow-shaped project tree for the nested-CV caller (reference experiment.py:924-1026)
+# ----------------------------------------------------------------------------------------
+
+
+class FakeDataset:
+    def __init__(self, patients):
+        self._patients = patients
+
+    def patients(self):
+        return dict(self._patients)
+
+
+class FakeProject:
+    """The two members of ``sf.Project`` the path touches: ``models_dir`` and ``dataset().patients()``."""
+
+    def __init__(self, models_dir, patients):
+        self.models_dir = models_dir
+        self._patients = patients
+
+    def dataset(self, verification=None):
+        return FakeDataset(self._patients)
+
+
+def _write_model(models_dir, idx, name, table, outcome, fmt, underscore):
+    """One trained-model folder as Slideflow lays it out: `<5-digit id>-<name>/` holding the validation
+    tile predictions (per-outcome column names, utils.py:19-28) and `slide_manifest.csv`."""
+    import os
+    folder = os.path.join(models_dir, f"{idx:05d}-{name}")
+    os.makedirs(folder, exist_ok=True)
+    sep = "_" if underscore else "-"
+    out = pd.DataFrame({
+        "slide": table["slide"],
+        f"{outcome}{sep}y_true0": table["y_true"],
+        f"{outcome}{sep}y_pred0": (1 - table["y_pred"]).astype(table["y_pred"].dtype),
+        f"{outcome}{sep}y_pred1": table["y_pred"],
+        f"{outcome}{sep}uncertainty0": table["uncertainty"],
+        f"{outcome}{sep}uncertainty1": table["uncertainty"],
+    })
+    if fmt == "csv":
+        out.to_csv(os.path.join(folder, "tile_predictions_val_epoch1.csv"), index=False)
+    else:
+        out.to_parquet(os.path.join(folder, "tile_predictions_val_epoch1.parquet.gzip"), compression="gzip")
+    slides = table["slide"].drop_duplicates().tolist()
+    with open(os.path.join(folder, "slide_manifest.csv"), "w") as f:
+        f.write("slide,dataset\n")
+        for i in range(3 * len(slides)):            # a model trains on more slides than it validates on
+            f.write(f"train{i:05d},training\n")
+        for sname in slides:
+            f.write(f"{sname},validation\n")
+    return folder
+
+
+def nested_cv_project(root, label="EXP_AA_UQ", outcome="cohort", outer_k=3, inner_k=5, n_slides=40,
+                      tiles_per_slide=50, seed0=500, fmt="csv", dtype=np.float32, underscore=False,
+                      slides_per_patient=2, missing_outer=()):
+    """Writes `outer_k` x `inner_k` inner-fold models (`{label}-k{k}`, kfold 1..inner_k) and `outer_k` outer
+    models (`{label}`, kfold k) under `root`/models and returns a FakeProject.  Tables come from
+    :func:`tile_table` with seeds seed0 + 100*k + j (j = 0 for the outer validation table).
+    Outer folds listed in `missing_outer` get no inner models (the reference skips them)."""
+    import os
+    models_dir = os.path.join(root, "models")
+    os.makedirs(models_dir, exist_ok=True)
+    patients = {}
+    idx = 1
+    for k in range(1, outer_k + 1):
+        outer = tile_table(n_slides, tiles_per_slide, seed=seed0 + 100 * k, dtype=dtype, prefix=f"o{k}s",
+                           slides_per_patient=slides_per_patient)
+        patients.update(patients_map(outer))
+        _write_model(models_dir, idx, f"{outcome}-{label}-HP0-kfold{k}", outer, outcome, fmt, underscore)
+        idx += 1
+        if k in missing_outer:
+            continue
+        for j in range(1, inner_k + 1):
+            inner = tile_table(n_slides, tiles_per_slide, seed=seed0 + 100 * k + j, dtype=dtype, prefix=f"i{k}{j}s",
+                               slides_per_patient=slides_per_patient)
+            patients.update(patients_map(inner))
+            _write_model(models_dir, idx, f"{outcome}-{label}-k{k}-HP0-kfold{j}", inner, outcome, fmt, underscore)
+            idx += 1
+    return FakeProject(models_dir, patients)
+
+
+# ----------------------------------------------------------------------------------------
 # image tiles
 # ----------------------------------------------------------------------------------------
 
