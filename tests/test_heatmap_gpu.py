@@ -1,0 +1,68 @@
+"""GPU tier: slide grid heat map + uncertainty masking (reference results.py:216-227, 257-264)."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def iface():
+    from biscuit_b200 import weights
+    from biscuit_b200.uq import UncertaintyInterface
+    it = UncertaintyInterface(weights.random_init(seed=1), max_batch=16)
+    yield it
+    it.close()
+
+
+def test_grid_scatter_and_mask(iface):
+    from biscuit_b200.heatmap import EMPTY, UQHeatmap
+    n = 11
+    tiles = synth.tiles_u8(n, seed=5)
+    rng = np.random.default_rng(0)
+    cells = rng.permutation(5 * 4)[:n]
+    grid = np.stack([cells % 5, cells // 5], axis=1)            # (x, y) on a 5 x 4 grid
+    hm = UQHeatmap(iface, tiles, grid, grid_shape=(5, 4), T=12, seed=3)
+    mean, std = iface.predict(tiles, T=12, seed=3)
+    assert hm.logits.shape == (4, 5, 2) and hm.uncertainty.shape == (4, 5, 2)
+    filled = np.zeros((4, 5), bool)
+    for i, (x, y) in enumerate(grid):
+        assert hm.logits[y, x].tobytes() == mean[i].tobytes()
+        assert hm.uncertainty[y, x].tobytes() == std[i].tobytes()
+        filled[y, x] = True
+    assert (hm.logits[~filled] == EMPTY).all() and (hm.uncertainty[~filled] == EMPTY).all()
+    thr = np.float64(np.median(std[:, 0]))
+    before = hm.logits.copy()
+    mask = hm.mask_uncertain(thr)
+    want = np.zeros((4, 5), bool)
+    for i, (x, y) in enumerate(grid):
+        want[y, x] = np.float64(std[i, 0]) > thr                 # strict >, float64 compare for an np.float64 threshold
+    assert (mask == want).all() and mask.sum() == (std[:, 0].astype(np.float64) > thr).sum()
+    assert (hm.logits[mask] == EMPTY).all() and (hm.logits[~mask] == before[~mask]).all()
+    excl, incl = hm.split_tiles(float(thr))
+    assert sorted(np.concatenate([excl, incl]).tolist()) == list(range(n))
+    assert (std[excl, 1] > np.float32(thr)).all() and not (std[incl, 1] > np.float32(thr)).any()
+    assert hm.tile_names()[0] == f"{std[0, 1]:.4f}-{grid[0, 0]}-{grid[0, 1]}.png"
+
+
+def test_grid_errors(iface):
+    from biscuit_b200.heatmap import UQHeatmap
+    tiles = np.zeros((2, 299, 299, 3), np.uint8)
+    with pytest.raises(ValueError):
+        UQHeatmap(iface, tiles, [[0, 0]])
+    with pytest.raises(ValueError):
+        UQHeatmap(iface, tiles, [[0, 0], [3, 1]], grid_shape=(2, 2))
+    with pytest.raises(ValueError):
+        UQHeatmap(iface, tiles, [[0, 0], [-1, 1]])
+
+
+def test_tile_uq_threshold_from_nested_cv(tmp_path):
+    from statistics import mean
+    from biscuit_b200.heatmap import tile_uq_threshold_from_nested_cv
+    from oracle import nested_cv_oracle as NO, threshold_oracle as O
+    project = synth.nested_cv_project(str(tmp_path), seed0=3100, n_slides=30, tiles_per_slide=60, fmt="parquet")
+    got = tile_uq_threshold_from_nested_cv(project, "cohort")
+    want = mean(O.from_cv(NO.df_from_cv(project, f"EXP_AA_UQ-k{k}", "cohort", 5), tile_uq="detect", slide_uq=None,
+                          patients=project.dataset().patients())["tile_uq"] for k in (1, 2, 3))
+    assert type(got) is type(want) and got == want
