@@ -20,6 +20,10 @@
 #include "dwpipe_sm100.cuh"
 #include "sepconv_sm100.cuh"
 #include "sepconv2d_sm100.cuh"
+#include "stain_sm100.cuh"
+
+int bq_stain_launch(bq_ctx* ctx, const uint8_t* tiles_dev, int64_t n, int32_t px, const float* lut_dev, float* stats_dev,
+                    const float target_means[3], const float target_stds[3], uint8_t* out_dev);   // stain.cu
 
 using bq::bf16;
 using bq::GemmParams;
@@ -246,6 +250,9 @@ struct bq_model {
   // buffers
   DevBuf tiles_dev;                            // uint8 staging [max_batch, px, px, 3] (double-buffered with tiles_dev2)
   DevBuf tiles_dev2;
+  int norm_kind = 0;                           // BQ_NORM_*: stain normalisation in front of the tile statistics
+  float norm_means[3] = {0, 0, 0}, norm_stds[3] = {1, 1, 1};
+  DevBuf tiles_norm, norm_lut, norm_stats;     // normalised micro-batch, gamma table, per-tile LAB statistics
   const uint8_t* tiles_src = nullptr;          // where stats / conv1 read the current micro-batch from
   cudaStream_t copy_stream = nullptr;          // H2D of micro-batch i+1 overlaps the backbone of micro-batch i
   cudaEvent_t copied[2] = {}, consumed[2] = {};
@@ -1076,6 +1083,12 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
         mdev = (const uint8_t*)m->masks_dev.p;
       }
     }
+    if (m->norm_kind == BQ_NORM_REINHARD_FAST) {
+      if ((rc = bq_stain_launch(ctx, m->tiles_src, nb, m->px, (const float*)m->norm_lut.p, (float*)m->norm_stats.p,
+                                m->norm_means, m->norm_stds, (uint8_t*)m->tiles_norm.p)))
+        return rc;
+      m->tiles_src = (const uint8_t*)m->tiles_norm.p;
+    }
     if ((rc = run_backbone(m, nb, nullptr, nullptr))) return rc;
     if (!tiles_on_dev) BQ_CUDA(ctx, cudaEventRecord(m->consumed[slot], ctx->stream));
     if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
@@ -1146,6 +1159,31 @@ int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const cha
   BQ_LAUNCH_CHECK(ctx);
   if ((rc = bq_from_device(ctx, out, scr, total * 4))) return rc;
   BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BQ_OK;
+}
+
+int bq_model_set_normalizer(bq_model* m, int32_t kind, const float target_means[3], const float target_stds[3]) {
+  if (!m) return BQ_ERR_ARG;
+  bq_ctx* ctx = m->ctx;
+  if (kind == BQ_NORM_NONE) { m->norm_kind = BQ_NORM_NONE; return BQ_OK; }
+  if (kind != BQ_NORM_REINHARD_FAST) return bq_fail(ctx, BQ_ERR_ARG, "bq_model_set_normalizer: unknown normaliser %d", kind);
+  if (!target_means || !target_stds) return bq_fail(ctx, BQ_ERR_ARG, "bq_model_set_normalizer: null target statistics");
+  for (int i = 0; i < 3; ++i) {
+    if (!(target_stds[i] > 0.f)) return bq_fail(ctx, BQ_ERR_ARG, "bq_model_set_normalizer: target_stds must be > 0");
+    m->norm_means[i] = target_means[i];
+    m->norm_stds[i] = target_stds[i];
+  }
+  BQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = bq_alloc(ctx, m->tiles_norm, (size_t)m->max_batch * m->px * m->px * 3)) ||
+      (rc = bq_alloc(ctx, m->norm_stats, (size_t)m->max_batch * 6 * sizeof(float))) ||
+      (rc = bq_alloc(ctx, m->norm_lut, 256 * sizeof(float))))
+    return rc;
+  float lut[256];
+  bq::stain::build_gamma_lut(lut);
+  BQ_CUDA(ctx, cudaMemcpyAsync(m->norm_lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice, ctx->stream));
+  BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->norm_kind = kind;
   return BQ_OK;
 }
 

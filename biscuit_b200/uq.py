@@ -53,10 +53,13 @@ class UncertaintyInterface:
         config: `ModelConfig` (default `hp.nature2022`).
         max_batch: tiles per backbone micro-batch held on the device.
         device: CUDA device index (default LOCAL_RANK or 0).
+        normalizer: None, 'reinhard_fast' (the reference's `hp.normalizer`, hp.py:19) or a
+            `norm.ReinhardFastNormalizer` carrying the fit; tiles are then stain-normalised on the GPU
+            in front of the per-image standardisation inside `predict`.
     """
 
     def __init__(self, weights: dict, config: ModelConfig = nature2022, max_batch: int = 64,
-                 device: int | None = None, ctx: _ffi.Context | None = None):
+                 device: int | None = None, ctx: _ffi.Context | None = None, normalizer=None):
         if config.model != "xception" or config.pooling != "avg" or config.include_top:
             raise ValueError("only the reference configuration (xception, avg pooling, include_top=False) is built")
         self.config = config
@@ -75,6 +78,26 @@ class UncertaintyInterface:
         _ffi.check(self.ctx.handle, self.lib.bq_model_load_weights(self.h, arr, len(weights)),
                    "bq_model_load_weights")
         del keep
+        if normalizer is not None:
+            self.set_normalizer(normalizer)
+
+    def set_normalizer(self, normalizer):
+        """Stain normalisation applied to every tile inside `predict` (None switches it off).  The
+        reference applies `interface.wsi_normalizer.rgb_to_rgb` itself before calling the interface
+        (results.py:251-254); callers that keep doing so must leave this unset."""
+        from . import norm
+        if isinstance(normalizer, str):
+            normalizer = norm.autoselect(normalizer)
+        if normalizer is None:
+            _ffi.check(self.ctx.handle, self.lib.bq_model_set_normalizer(self.h, norm.NORM_NONE, None, None),
+                       "bq_model_set_normalizer")
+        else:
+            tm = np.ascontiguousarray(normalizer.target_means, np.float32)
+            ts = np.ascontiguousarray(normalizer.target_stds, np.float32)
+            _ffi.check(self.ctx.handle,
+                       self.lib.bq_model_set_normalizer(self.h, int(normalizer.kind), _ffi.ptr(tm), _ffi.ptr(ts)),
+                       "bq_model_set_normalizer")
+        self.normalizer = normalizer
 
     def close(self):
         if getattr(self, "h", None):

@@ -185,6 +185,21 @@ enum {
 int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flops[BQ_PROFILE_KINDS],
                             double bytes[BQ_PROFILE_KINDS], int64_t launches[BQ_PROFILE_KINDS]);
 
+/* ------------------------------------------------------------------------------------------------
+ * stain normalisation in front of per-image standardisation
+ *   replaces `interface.wsi_normalizer.rgb_to_rgb(image)` (results.py:251-254) for hp.normalizer ==
+ *   'reinhard_fast' (biscuit/hp.py:19); arithmetic restated from slideflow/norm/tensorflow/reinhard.py
+ * ---------------------------------------------------------------------------------------------- */
+enum { BQ_NORM_NONE = 0, BQ_NORM_REINHARD_FAST = 1 };
+/* tiles, out: uint8 NHWC [n, px, px, 3] (host or device); target_means / target_stds: the fitted LAB
+ * statistics of the reference image (3 floats each, host); lab_stats: nullable float32 [n, 6] =
+ * per-tile {mean L, a, b, std L, a, b} of the SOURCE tiles (host or device). */
+int bq_stain_normalize(bq_ctx* ctx, int32_t kind, const uint8_t* tiles, int64_t n, int32_t px,
+                       const float target_means[3], const float target_stds[3], uint8_t* out,
+                       float* lab_stats);
+/* Make bq_predict_uq normalise every tile first (kind = BQ_NORM_NONE switches it off again). */
+int bq_model_set_normalizer(bq_model* m, int32_t kind, const float target_means[3], const float target_stds[3]);
+
 /* Developer hook (hardware probe, not on the product path): one 128x16x16 tcgen05.mma whose A operand starts `shift`
  * rows into a 128B-swizzled [rows x 64] bf16 tile, channel group cg, against an identity B in the no-swizzle layout;
  * base_offset_mode 1 sets the descriptor base_offset field to (addr >> 7) & 7.  out = float [128][16]. */
