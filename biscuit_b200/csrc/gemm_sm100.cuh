@@ -496,16 +496,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // Only the leader's warp 1 issues MMAs; each CTA runs its own TMA producer and its own epilogue on its
 // 128 accumulator rows.
 // =====================================================================================================
-constexpr int k2Stages = 4;
+constexpr int k2Stages = 4;                          // operand ring depth with a residual operand; 5 without (smem permitting)
 constexpr int k2EpiWarps = 8;                        // two warps per TMEM lane quadrant (32 columns of a chunk each)
 constexpr int k2Threads = 64 + 32 * k2EpiWarps;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
 constexpr int k2MaxN = 2048;
 constexpr int k2ResBufs = 3;                         // residual chunks in flight (prefetch distance 2)                         // per-channel scale/shift staged in smem for the whole N
+template <int STAGES>
 struct SmemPlan2 {
   static constexpr int kABytes = kBM * 64 * 2;                 // 16 KB
   static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (half of the N tile)
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutOffset = k2Stages * kStageBytes;
+  static constexpr int kOutOffset = STAGES * kStageBytes;
   static constexpr int kScaleOffset = kOutOffset + 2 * kEpiBytes;           // float scale[k2MaxN], shift[k2MaxN]
   static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
   static constexpr int kResOffset = kBarOffset + 1024;                      // residual staging LAST: only requested when used
@@ -560,12 +561,12 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                : "memory");
 }
 
-static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                          const GemmParams p) {
-  using Plan = SmemPlan2;
-  constexpr int STAGES = k2Stages;
+  using Plan = SmemPlan2<STAGES>;
   constexpr int BLOCK_K = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -340,8 +340,13 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
   } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
     const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
     int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
-    gemm_tcgen05_2cta_kernel<<<2 * clusters, k2Threads, gp.residual ? SmemPlan2::kTotal : SmemPlan2::kTotalNoRes, ctx->stream>>>(
-        ta, *tb_half, tc, tr, gp);
+    // a deeper operand ring where no residual staging is needed (the ring is what hides the DRAM round trip of A)
+    if (gp.residual)
+      gemm_tcgen05_2cta_kernel<k2Stages><<<2 * clusters, k2Threads, SmemPlan2<k2Stages>::kTotal, ctx->stream>>>(
+          ta, *tb_half, tc, tr, gp);
+    else
+      gemm_tcgen05_2cta_kernel<k2Stages + 1><<<2 * clusters, k2Threads, SmemPlan2<k2Stages + 1>::kTotalNoRes, ctx->stream>>>(
+          ta, *tb_half, tc, tr, gp);
   } else if (m->gemm_direct_epi) {
     gemm_tcgen05_kernel<64, false><<<grid, kThreads, SmemPlan<64, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else {
@@ -866,8 +871,10 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
   m->gemm_direct_epi = g && strcmp(g, "direct") == 0;   // debug switch: per-thread global stores in the epilogue
   m->gemm_2cta = !(g && (strcmp(g, "1cta") == 0 || strcmp(g, "direct") == 0));   // default: cta_group::2 pairs
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan2::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan2<bq::sm100::k2Stages>::kTotal);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan2<bq::sm100::k2Stages + 1>::kTotalNoRes);
   const char* hv = getenv("BQ_HEAD");
   m->head_fused = !(hv && strcmp(hv, "unfused") == 0) &&   // debug switch: three-kernel head (expand / GEMM / final)
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
