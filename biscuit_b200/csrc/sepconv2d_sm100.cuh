@@ -87,9 +87,9 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_out);
-    for (int s = 0; s < kPStages; ++s) { mbar_init(patch_full(s), 1); mbar_init(patch_empty(s), kProducerWarps); }
+    for (int s = 0; s < kPStages; ++s) { mbar_init(patch_full(s), 1); mbar_init(patch_empty(s), kProducerWarps / 2); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_full(s), kProducerWarps); mbar_init(a_empty(s), 1);
+      mbar_init(a_full(s), kProducerWarps / 2); mbar_init(a_empty(s), 1);
       mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1);
       mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8);
     }
@@ -216,16 +216,18 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
     }
     if (leader) tma_store_wait_all();
   } else {
-    // ===================== depthwise producers: thread = (4 channels, patch column), walks down 8 rows =====================
+    // ===================== depthwise producers =====================
+    // Two groups of four warps take alternate k-blocks (group g owns A stage g); a thread = (4 channels, TWO adjacent
+    // patch columns) walks down the 8 rows with the 3x4 input window in registers: 4 LDS.64 per row for two outputs
+    // instead of 6, four independent FFMA2 accumulator chains.
     const int ptid = threadIdx.x - 320;                         // 0..255
-    const int c4 = ptid & 15, px = ptid >> 4;                   // channel group, column 0..15
-    int ps = 0; uint32_t pph = 0;
-    int as = 0; uint32_t aph = 0;
-    auto load3 = [&](const uint8_t* rowp, float2 (&d)[3][2]) {  // pixels px-1, px, px+1 of one halo row
+    const int grp = ptid >> 7, tg = ptid & 127;
+    const int c4 = tg & 15, pair = tg >> 4;                     // channel group, column pair 0..7
+    auto load4 = [&](const uint8_t* rowp, float2 (&d)[4][2]) {  // halo pixels 2*pair .. 2*pair+3 of one halo row
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < 4; ++k) {
         uint2 raw = *(const uint2*)(rowp + (size_t)k * 128);
-        if (RELU_IN) {                                            // ReLU on the packed bf16 pairs (2 instead of 4 instructions)
+        if (RELU_IN) {                                            // ReLU on the packed bf16 pairs
           const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
           __nv_bfloat162* hb = (__nv_bfloat162*)&raw;
           hb[0] = __hmax2(hb[0], z2);
@@ -235,48 +237,67 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
         d[k][1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
       }
     };
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int c = kb * 64 + c4 * 4;
-        float2 w[9][2];
+    const int total_kb = ((n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * num_kb;   // this CTA's k-blocks
+    for (int q = grp; q < total_kb; q += 2) {
+      const int kb = q % num_kb;
+      const int ps = q % kPStages;
+      const uint32_t pph = (uint32_t)(q / kPStages) & 1u, aph = (uint32_t)(q >> 1) & 1u;
+      const int c = kb * 64 + c4 * 4;
+      float2 w[9][2];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 wv = __ldg((const float4*)(p.dw + (size_t)t * p.K + c));
-          w[t][0] = make_float2(wv.x, wv.y);
-          w[t][1] = make_float2(wv.z, wv.w);
-        }
-        mbar_wait(patch_full(ps), pph);
-        mbar_wait(a_empty(as), aph ^ 1u);
-        const uint8_t* col = smem_gen + kOffPatch + ps * kPatchBytes + (size_t)px * 128 + c4 * 8;   // halo (row 0, col px)
-        uint8_t* a_dst = smem_gen + kOffA + as * kABytes;
-        float2 ra[3][2], rb[3][2], rc[3][2];
-        load3(col, ra);
-        load3(col + (size_t)kHW * 128, rb);
-        auto step = [&](const float2 (&r0)[3][2], const float2 (&r1)[3][2], float2 (&r2)[3][2], int py) {
-          load3(col + (size_t)(py + 2) * kHW * 128, r2);
-          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      for (int t = 0; t < 9; ++t) {
+        const float4 wv = __ldg((const float4*)(p.dw + (size_t)t * p.K + c));
+        w[t][0] = make_float2(wv.x, wv.y);
+        w[t][1] = make_float2(wv.z, wv.w);
+      }
+      mbar_wait(patch_full(ps), pph);
+      mbar_wait(a_empty(grp), aph ^ 1u);
+      const uint8_t* col = smem_gen + kOffPatch + ps * kPatchBytes + (size_t)(2 * pair) * 128 + c4 * 8;   // halo (row 0, col 2*pair)
+      uint8_t* a_dst = smem_gen + kOffA + grp * kABytes;
+      float2 ra[4][2], rb[4][2], rc[4][2];
+      load4(col, ra);
+      load4(col + (size_t)kHW * 128, rb);
+      auto step = [&](const float2 (&r0)[4][2], const float2 (&r1)[4][2], float2 (&r2)[4][2], int py) {
+        load4(col + (size_t)(py + 2) * kHW * 128, r2);
+        float2 a[2][2];
+        a[0][0] = a[0][1] = a[1][0] = a[1][1] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r0[kx][0], w[kx][0], a0); a1 = __ffma2_rn(r0[kx][1], w[kx][1], a1); }
+        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r1[kx][0], w[3 + kx][0], a0); a1 = __ffma2_rn(r1[kx][1], w[3 + kx][1], a1); }
+          for (int h = 0; h < 2; ++h) {
+            a[0][h] = __ffma2_rn(r0[kx][h], w[kx][h], a[0][h]);
+            a[1][h] = __ffma2_rn(r0[kx + 1][h], w[kx][h], a[1][h]);
+          }
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r2[kx][0], w[6 + kx][0], a0); a1 = __ffma2_rn(r2[kx][1], w[6 + kx][1], a1); }
-          const int r = py * kPW + px;                           // A row of this output pixel
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            a[0][h] = __ffma2_rn(r1[kx][h], w[3 + kx][h], a[0][h]);
+            a[1][h] = __ffma2_rn(r1[kx + 1][h], w[3 + kx][h], a[1][h]);
+          }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            a[0][h] = __ffma2_rn(r2[kx][h], w[6 + kx][h], a[0][h]);
+            a[1][h] = __ffma2_rn(r2[kx + 1][h], w[6 + kx][h], a[1][h]);
+          }
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          const int r = py * kPW + 2 * pair + cx;                 // A row of this output pixel
           uint2 o;
           __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-          ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
-          ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
+          ob[0] = __floats2bfloat162_rn(a[cx][0].x, a[cx][0].y);
+          ob[1] = __floats2bfloat162_rn(a[cx][1].x, a[cx][1].y);
           *(uint2*)(a_dst + (size_t)r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8) = o;
-        };
-        step(ra, rb, rc, 0); step(rb, rc, ra, 1); step(rc, ra, rb, 2);
-        step(ra, rb, rc, 3); step(rb, rc, ra, 4); step(rc, ra, rb, 5);
-        step(ra, rb, rc, 6); step(rb, rc, ra, 7);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(a_full(as)); mbar_arrive(patch_empty(ps)); }
-        if (++ps == kPStages) { ps = 0; pph ^= 1u; }
-        if (++as == 2) { as = 0; aph ^= 1u; }
-      }
+        }
+      };
+      step(ra, rb, rc, 0); step(rb, rc, ra, 1); step(rc, ra, rb, 2);
+      step(ra, rb, rc, 3); step(rb, rc, ra, 4); step(rc, ra, rb, 5);
+      step(ra, rb, rc, 6); step(rb, rc, ra, 7);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a_full(grp)); mbar_arrive(patch_empty(ps)); }
     }
   }
   tc_fence_before();
