@@ -69,11 +69,17 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   bool owned = false;
+  bool pooled = false;               // allocated with cudaMallocAsync on `stream` (short-lived per-call buffers)
+  cudaStream_t stream = nullptr;
   void release() {
-    if (owned && p) cudaFree(p);
+    if (owned && p) {
+      // stream-ordered free: no device-wide synchronisation (cudaFree costs ~1 ms per buffer with work in flight)
+      if (!pooled || cudaFreeAsync(p, stream) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+    }
     p = nullptr;
     bytes = 0;
     owned = false;
+    pooled = false;
   }
   ~DevBuf() { release(); }
   DevBuf() = default;
@@ -105,6 +111,36 @@ inline int bq_alloc(bq_ctx* ctx, DevBuf& dst, size_t bytes) {
   BQ_CUDA(ctx, cudaMalloc(&dst.p, bytes));
   dst.bytes = bytes;
   dst.owned = true;
+  return BQ_OK;
+}
+
+// Stream-ordered variants for per-call temporaries (thresholding tables, ROC operands): allocation and release are
+// queued on the ctx stream and served from the device's default memory pool, whose release threshold bq_create raises
+// so the memory stays cached between calls.
+inline int bq_alloc_pooled(bq_ctx* ctx, DevBuf& dst, size_t bytes) {
+  if (dst.owned && dst.bytes >= bytes) return BQ_OK;
+  dst.release();
+  if (bytes == 0) return BQ_OK;
+  BQ_CUDA(ctx, cudaMallocAsync(&dst.p, bytes, ctx->stream));
+  dst.bytes = bytes;
+  dst.owned = true;
+  dst.pooled = true;
+  dst.stream = ctx->stream;
+  return BQ_OK;
+}
+
+inline int bq_to_device_pooled(bq_ctx* ctx, DevBuf& dst, const void* src, size_t bytes) {
+  dst.release();
+  if (bytes == 0) return BQ_OK;
+  if (bq_is_device_ptr(src)) {
+    dst.p = const_cast<void*>(src);
+    dst.bytes = bytes;
+    dst.owned = false;
+    return BQ_OK;
+  }
+  int rc = bq_alloc_pooled(ctx, dst, bytes);
+  if (rc) return rc;
+  BQ_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return BQ_OK;
 }
 

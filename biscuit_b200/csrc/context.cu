@@ -45,6 +45,14 @@ int bq_create(int device, bq_ctx** out) {
     delete ctx;
     return BQ_ERR_CUDA;
   }
+  // keep memory freed by cudaFreeAsync cached in the default pool (per-call thresholding temporaries are re-allocated
+  // on every apply / detect; trimming the pool at each synchronisation would turn them back into cudaMalloc calls)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
   *out = ctx;
   return BQ_OK;
 }

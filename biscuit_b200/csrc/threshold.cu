@@ -592,10 +592,10 @@ int bq_table_create(bq_ctx* ctx, int64_t n, int dtype, const void* y_pred, const
   bq_table* t = new bq_table();
   t->ctx = ctx; t->n = n; t->dtype = dtype;
   int rc;
-  if ((rc = bq_to_device(ctx, t->y_pred, y_pred, n * elem(dtype))) ||
-      (rc = bq_to_device(ctx, t->unc, uncertainty, n * elem(dtype))) ||
-      (rc = bq_to_device(ctx, t->y_true, y_true, n)) ||
-      (rc = bq_alloc(ctx, t->incorrect, n > 0 ? n : 1))) {
+  if ((rc = bq_to_device_pooled(ctx, t->y_pred, y_pred, n * elem(dtype))) ||
+      (rc = bq_to_device_pooled(ctx, t->unc, uncertainty, n * elem(dtype))) ||
+      (rc = bq_to_device_pooled(ctx, t->y_true, y_true, n)) ||
+      (rc = bq_alloc_pooled(ctx, t->incorrect, n > 0 ? n : 1))) {
     delete t;
     return rc;
   }
@@ -620,9 +620,9 @@ int bq_table_set_groups(bq_table* t, const int32_t* codes, int32_t n_groups) {
   t->groups_ready = false;
   t->n_groups = n_groups;
   int rc;
-  if ((rc = bq_to_device(ctx, t->codes, codes, t->n * 4))) return rc;
+  if ((rc = bq_to_device_pooled(ctx, t->codes, codes, t->n * 4))) return rc;
   const size_t L = n_groups > 0 ? n_groups : 1;
-  if ((rc = bq_alloc(ctx, t->seg_begin, L * 8)) || (rc = bq_alloc(ctx, t->seg_end, L * 8))) return rc;
+  if ((rc = bq_alloc_pooled(ctx, t->seg_begin, L * 8)) || (rc = bq_alloc_pooled(ctx, t->seg_end, L * 8))) return rc;
   void* scr = nullptr;
   if ((rc = bq_scratch(ctx, L * 4 + 256, &scr))) return rc;
   int32_t* runs = (int32_t*)scr;
@@ -644,7 +644,7 @@ int bq_table_set_groups(bq_table* t, const int32_t* codes, int32_t n_groups) {
       // groups interleave in row order: stable radix sort of (code -> row) restores per-group row order
       t->contiguous = false;
       const int64_t n = t->n;
-      if ((rc = bq_alloc(ctx, t->perm, n * 4)) || (rc = bq_alloc(ctx, t->sorted_codes, n * 4))) return rc;
+      if ((rc = bq_alloc_pooled(ctx, t->perm, n * 4)) || (rc = bq_alloc_pooled(ctx, t->sorted_codes, n * 4))) return rc;
       size_t tmp_bytes = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                       (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 32, ctx->stream);
@@ -754,8 +754,8 @@ int bq_roc(bq_ctx* ctx, const void* score, int dtype, const uint8_t* label, cons
   BQ_CUDA(ctx, cudaSetDevice(ctx->device));
   DevBuf s, l, inc;
   int rc;
-  if ((rc = bq_to_device(ctx, s, score, n * elem(dtype))) || (rc = bq_to_device(ctx, l, label, n))) return rc;
-  if (include && (rc = bq_to_device(ctx, inc, include, n))) return rc;
+  if ((rc = bq_to_device_pooled(ctx, s, score, n * elem(dtype))) || (rc = bq_to_device_pooled(ctx, l, label, n))) return rc;
+  if (include && (rc = bq_to_device_pooled(ctx, inc, include, n))) return rc;
   if (dtype == BQ_F32)
     rc = roc_run<float>(ctx, (const float*)s.p, (const uint8_t*)l.p, (const uint8_t*)inc.p, n, out);
   else
@@ -825,8 +825,8 @@ int bq_group_apply(bq_ctx* ctx, int64_t L, int dtype, const void* g_pred, const 
   const size_t es = elem(dtype);
   DevBuf p, u, y;
   int rc;
-  if ((rc = bq_to_device(ctx, p, g_pred, L * es)) || (rc = bq_to_device(ctx, u, g_unc, L * es)) ||
-      (rc = bq_to_device(ctx, y, g_true, L)))
+  if ((rc = bq_to_device_pooled(ctx, p, g_pred, L * es)) || (rc = bq_to_device_pooled(ctx, u, g_unc, L * es)) ||
+      (rc = bq_to_device_pooled(ctx, y, g_true, L)))
     return rc;
   size_t o_e = 0, o_c = bq_align_up(L * es, 256), o_i = o_c + bq_align_up(L, 256), o_b = o_i + bq_align_up(L, 256),
          o_inc = o_b + bq_align_up(L, 256), o_conf = o_inc + bq_align_up(L, 256), total = o_conf + 256;

@@ -225,7 +225,7 @@ def _tile_stage(tab: _DeviceTable, df, pred_thresh, patients):
             raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
         log.debug(f"Using tile prediction threshold: {pred_thresh:.4f}")  # :161
     if patients is not None:                                          # :163-166
-        df["patient"] = df["slide"].map(patients)
+        df["patient"] = _map_slides(tab, df, patients)
     else:
         log.debug("Patients not provided; assuming 1:1 slide:patient mapping")
     err, cor, ybin = tab.tile_process(_cmp_scalar(pred_thresh, df["y_pred"].to_numpy().dtype))
@@ -236,6 +236,18 @@ def _tile_stage(tab: _DeviceTable, df, pred_thresh, patients):
     df["incorrect"] = (cor ^ 1).astype(int)                           # :175
     df["y_pred_bin"] = ybin.astype(int)                               # :176
     return pred_thresh
+
+
+def _map_slides(tab, df, patients):
+    """``df['slide'].map(patients)`` computed on the UNIQUE slide names and expanded through the factorisation
+    codes (same `Series.map` on the same values, so the same dtype inference and NaN for unknown slides), instead
+    of a hash lookup per tile row; the factorisation is kept on the table for the slide-level grouping."""
+    codes, uniques = _factorize(df["slide"])
+    tab.slide_factorized = (codes, uniques)
+    if len(codes) == 0 or codes.min() < 0:                            # NaN slide names: leave it to pandas
+        return df["slide"].map(patients)
+    mapped = pd.Series(uniques, dtype=df["slide"].dtype).map(patients)
+    return pd.Series(mapped.array.take(codes), index=df.index)
 
 
 def process_tile_predictions(df, pred_thresh=0.5, patients=None):
@@ -260,6 +272,8 @@ def _factorize(keys: pd.Series):
 def _group_stage(tab: _DeviceTable, df, level, tile_uq_eff, pred_thresh, factorized=None):
     """threshold.py:188-245 with the tile-UQ filter (threshold.py:298/412/426) applied on the
     device.  Returns (group DataFrame, pred_thresh used)."""
+    if factorized is None and level == "slide":
+        factorized = getattr(tab, "slide_factorized", None)          # already factorised for the patient mapping
     codes, uniques = factorized if factorized is not None else _factorize(df[level])
     tab.set_groups(codes, len(uniques))
     tab.set_filter(tile_uq_eff)
