@@ -107,16 +107,22 @@ depthwise3x3_pipe_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W
     return;
   }
 
-  // ===================== compute groups: group g takes the CTA's items g, g + 3, g + 6, ... =====================
+  // ===================== compute groups: group g computes the CTA's items g, g + 3, g + 6, ... =====================
   const int g = (threadIdx.x - 32) / kGroupThreads, tg = (threadIdx.x - 32) % kGroupThreads;
   constexpr int cpc = CC >> 2;
   const int c4 = tg % cpc, pair = tg / cpc;
   constexpr uint32_t row_bytes = (uint32_t)kHalo * CC * 2;
-  for (int j = g;; j += kGroups) {
+  for (int j = 0;; ++j) {
     const int it = blockIdx.x + j * gridDim.x;
     if (it >= n_items) break;
     const int s = j % kStages;
     const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+    // Every warp observes EVERY fill of every stage in order, also those of the other groups' items.  A parity wait
+    // only distinguishes "the previous phase" from "this phase": a warp that skipped a stage's intermediate fills
+    // (3 groups share 4 stages) and ran ahead -- the fifth warp of a group has no active lane on 18-column tiles
+    // with CC = 56 -- passed the wait while the barrier was still one phase behind, read a stage in flux and then
+    // released it (seen as run-to-run differences in column 18 of ~5 % of the 37x37 tiles).
+    if (j % kGroups != g) { mbar_wait(full_bar(s), ph); continue; }
     const int chunk = it % chunks, t = (it / chunks) % tiles, img = it / (chunks * tiles);
     const int ty0 = (t / tiles_x) * kTile, tx0 = (t % tiles_x) * kTile;
     const int th = min(kTile, H - ty0), tw = min(kTile, W - tx0);
@@ -188,6 +194,9 @@ depthwise3x3_pipe_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W
         if (py + 2 < th) step(rc, ra, rb);
       }
     }
+    // The stage was read through the generic proxy (ld.shared) and will be overwritten through the async proxy (TMA):
+    // every reading thread orders its loads ahead of that write before the warp releases the stage.
+    fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));                     // this warp no longer reads stage s
   }

@@ -446,6 +446,7 @@ int build_plan(bq_model* m) {
   int H = s2, C = 64;
 
   int dw_rc = BQ_OK;
+  int n_dw = 0;
   auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
     Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
     op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
@@ -457,6 +458,8 @@ int build_plan(bq_model* m) {
     r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kTile, bq::dwtc::kTile, 64, true);
     if (r && !dw_rc) dw_rc = r;
     op.bdiag = (const bf16*)sw.bdiag.p;
+    op.tag = "dw" + std::to_string(n_dw++);          // debug-stage name of the n-th stand-alone depthwise output
+    op.Ho = h; op.Wo = h; op.Cout = c;
     m->plan.push_back(op);
   };
   auto add_gemm = [&](const bf16* a, int rows, const PwWeights& w, bf16* out, int relu, const bf16* resid, int stage,
