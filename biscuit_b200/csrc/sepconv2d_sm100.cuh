@@ -250,6 +250,9 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
         w[t][0] = make_float2(wv.x, wv.y);
         w[t][1] = make_float2(wv.z, wv.w);
       }
+      // observe EVERY patch fill in order, also the other group's (q - 1): with an odd ring depth a group sees only
+      // every other phase of a stage's barrier, and a parity wait cannot tell "one phase behind" from "done"
+      if (q > 0) mbar_wait(patch_full((q - 1) % kPStages), (uint32_t)((q - 1) / kPStages) & 1u);
       mbar_wait(patch_full(ps), pph);
       mbar_wait(a_empty(grp), aph ^ 1u);
       const uint8_t* col = smem_gen + kOffPatch + ps * kPatchBytes + (size_t)(2 * pair) * 128 + c4 * 8;   // halo (row 0, col 2*pair)
