@@ -252,3 +252,23 @@ def test_depthwise_generations_bit_identical():
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
         outs.append(np.load(path))
     assert outs[0].tobytes() == outs[1].tobytes(), f"max |d| = {np.abs(outs[0] - outs[1]).max()}"
+
+
+def test_results_do_not_depend_on_micro_batch():
+    """A tile's features / mean / std are a function of (tile, global tile index, seed) only: bit-identical for
+    micro-batches of 96 and 256 tiles (different GEMM M tiling, different SM assignment, partial last batch)."""
+    import torch
+    from biscuit_b200.uq import UncertaintyInterface
+    from biscuit_b200.weights import random_init
+    n = 330
+    t = torch.from_numpy(synth.tiles_u8(66, seed=6)).cuda().repeat(5, 1, 1, 1).contiguous()
+    outs = []
+    for B in (96, 256):
+        it = UncertaintyInterface(random_init(seed=1), max_batch=B)
+        try:
+            outs.append(it.predict(t, T=9, seed=8, return_features=True))
+        finally:
+            it.close()
+    for a, b, name in zip(outs[0], outs[1], ("mean", "std", "features")):
+        bad = np.nonzero(np.abs(a - b).reshape(n, -1).max(1) > 0)[0]
+        assert a.tobytes() == b.tobytes(), f"{name}: {len(bad)} tiles depend on the micro-batch size, first {bad[:8]}"
