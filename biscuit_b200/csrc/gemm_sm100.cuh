@@ -848,9 +848,12 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
       const int me = warp == 1 ? 0 : 1;
       int li = 0;                                           // local tile index of this CTA
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
-        if ((li & 1) != me) continue;
         const int s = li % kC2Stages, as = li % kC2AccStages;
         const uint32_t ph = (uint32_t)(li / kC2Stages) & 1u, aph = (uint32_t)(li / kC2AccStages) & 1u;
+        // the other warp's tile: still OBSERVE its window fill.  With 3 stages and 2 issuers a warp would otherwise see
+        // only every other phase of a stage's barrier, and a parity wait cannot tell "one phase behind" from "done"
+        // (the aliasing that bit the depthwise ring)
+        if ((li & 1) != me) { mbar_wait(full_bar(s), ph); continue; }
         mbar_wait(tempty_bar(as), aph ^ 1u);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
