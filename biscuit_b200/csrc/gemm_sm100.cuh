@@ -501,11 +501,13 @@ constexpr int k2EpiWarps = 8;                        // two warps per TMEM lane 
 constexpr int k2Threads = 64 + 32 * k2EpiWarps;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
 constexpr int k2MaxN = 2048;
 constexpr int k2ResBufs = 3;                         // residual chunks in flight (prefetch distance 2)                         // per-channel scale/shift staged in smem for the whole N
-template <int STAGES>
+constexpr int k2WideN = 384;                         // WIDE: one 256 x 384 accumulator per CTA pair (256 + 128 columns, two MMAs per k-step)
+template <int STAGES, bool WIDE = false>
 struct SmemPlan2 {
   static constexpr int kABytes = kBM * 64 * 2;                 // 16 KB
-  static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (half of the N tile)
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (this CTA's half of the first 256 columns)
+  static constexpr int kB2Bytes = WIDE ? 64 * 64 * 2 : 0;      // 8 KB (this CTA's half of columns 256..383)
+  static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
   static constexpr int kOutOffset = STAGES * kStageBytes;
   static constexpr int kScaleOffset = kOutOffset + 2 * kEpiBytes;           // float scale[k2MaxN], shift[k2MaxN]
   static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
@@ -561,13 +563,23 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                : "memory");
 }
 
-template <int STAGES>
+// WIDE (N in (640, 768], no residual -- the 728-wide pointwise convs): the pair tile is 256 x 384 instead of 256 x 256, so the
+// A rows are fetched twice per M tile instead of three times and a k-block moves 40 KB per CTA for 1.5x the MMA work
+// (the 256-wide tile is L2-throughput-bound).  384 fp32 columns leave no room for a second
+// accumulator stage in the 512 TMEM columns, so the epilogue of a tile does not overlap the next tile's MMAs; the operand ring
+// keeps filling meanwhile.  Columns 256.. come from a second MMA per k-step (UMMA N <= 256) on a second B sub-tile
+// (tmap_b2: 64-row boxes), so accumulator column c is global column n0 + c.
+// MEASURED: correct (passes the model parity suite) but 8 % SLOWER than the 256-wide double-buffered kernel (69.4 vs 64.5 ms
+// of pointwise GEMM per 4096 tiles): losing the epilogue/MMA overlap costs more than the saved operand traffic.  Kept as an
+// experiment switch (BQ_GEMM_WIDE=on), off by default.
+template <int STAGES, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                         const GemmParams p) {
-  using Plan = SmemPlan2<STAGES>;
+                         const __grid_constant__ CUtensorMap tmap_b2, const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
+  using Plan = SmemPlan2<STAGES, WIDE>;
   constexpr int BLOCK_K = 64;
+  constexpr int ACC = WIDE ? 1 : kAccStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -589,12 +601,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int n_tiles = (p.N + p.bn_box - 1) / p.bn_box;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const uint32_t b_box_bytes = (uint32_t)(p.bn_box / 2) * BLOCK_K * 2;
-  const uint32_t stage_tx = 2u * (Plan::kABytes + b_box_bytes);     // both CTAs' bytes land on the leader's barrier
+  const uint32_t b_box_bytes = WIDE ? (uint32_t)Plan::kBBytes : (uint32_t)(p.bn_box / 2) * BLOCK_K * 2;
+  const uint32_t stage_tx = 2u * (Plan::kABytes + b_box_bytes + Plan::kB2Bytes);     // both CTAs' bytes land on the leader's barrier
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (WIDE) tma_prefetch_desc(&tmap_b2);
     tma_prefetch_desc(&tmap_out);
     if (p.residual) tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
@@ -625,8 +638,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int n0 = (tile % n_tiles) * p.bn_box;
         int n_cols = p.N - n0;
         if (n_cols > p.bn_box) n_cols = p.bn_box;
-        n_cols = (n_cols + 15) & ~15;
-        const int nb0 = n0 + (int)rank * (n_cols / 2);            // this CTA's half of the N tile
+        n_cols = WIDE ? ((n_cols + 31) & ~31) : ((n_cols + 15) & ~15);
+        // this CTA's half of the N tile (WIDE: of its first 256 columns, and of the columns from 256 on)
+        const int nb0 = WIDE ? n0 + (int)rank * 128 : n0 + (int)rank * (n_cols / 2);
+        const int nb1 = n0 + 256 + (int)rank * ((n_cols - 256) / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (is_leader) mbar_expect_tx(full_bar(s), stage_tx);
@@ -634,6 +649,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t a_dst = smem_base + s * Plan::kStageBytes, b_dst = a_dst + Plan::kABytes;
           tma_load_2d_2cta(a_dst, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
           tma_load_2d_2cta(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, nb0);
+          if (WIDE) tma_load_2d_2cta(b_dst + Plan::kBBytes, &tmap_b2, full_bar(s), kb * BLOCK_K, nb1);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -647,8 +663,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int n0 = (tile % n_tiles) * p.bn_box;
         int n_cols = p.N - n0;
         if (n_cols > p.bn_box) n_cols = p.bn_box;
-        n_cols = (n_cols + 15) & ~15;
-        const uint32_t idesc = make_idesc(2 * kBM, n_cols);
+        n_cols = WIDE ? ((n_cols + 31) & ~31) : ((n_cols + 15) & ~15);
+        const uint32_t idesc = make_idesc(2 * kBM, WIDE ? 256 : n_cols);
+        const uint32_t idesc2 = make_idesc(2 * kBM, WIDE ? n_cols - 256 : 16);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
@@ -659,13 +676,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           int ksteps = BLOCK_K / 16;
           if (kb == num_kb - 1) ksteps = (p.K - kb * BLOCK_K + 15) / 16;
           const uint64_t da = make_smem_desc<128>(a_src), db = make_smem_desc<128>(b_src);
-          for (int k = 0; k < ksteps; ++k)
+          const uint64_t db2 = make_smem_desc<128>(b_src + Plan::kBBytes);
+          for (int k = 0; k < ksteps; ++k) {
             umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + (uint64_t)(2 * k), db2 + (uint64_t)(2 * k), idesc2, (kb | k) ? 1u : 0u);
+          }
           umma_commit_2cta(empty_bar(s));
           if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(as));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        if (++as == kAccStages) { as = 0; aph ^= 1u; }
+        if (++as == ACC) { as = 0; aph ^= 1u; }
       }
     }
   } else {
@@ -763,7 +783,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(as), 0);     // accumulator stage drained -> leader's barrier
-      if (++as == kAccStages) { as = 0; aph ^= 1u; }
+      if (++as == ACC) { as = 0; aph ^= 1u; }
     }
     if (leader) tma_store_wait_all();
   }

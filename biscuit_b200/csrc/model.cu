@@ -213,6 +213,7 @@ struct Op {
   int blk_k = 64;
   CUtensorMap ta, tb, tc, tr; // A, B, output, residual
   CUtensorMap tb2;            // B with a half-height box (2-CTA kernel: each CTA stages N/2 rows)
+  CUtensorMap tb3;            // B with a 64-row box (WIDE 2-CTA kernel: columns 256.. of a 384-wide tile)
 };
 
 struct Arena {                // activation scratch: a handful of max-size buffers
@@ -237,6 +238,7 @@ struct bq_model {
   bool use_graph = true;
   cudaGraphExec_t backbone_graph = nullptr;
   int64_t graph_kernels = 0;                   // kernel launches one replay stands for (bq_launch_count bookkeeping)
+  bool gemm_wide = false;                      // experiment: 256 x 384 pair tiles for the 728-wide pointwise convs (BQ_GEMM_WIDE=on); slower
   bool sep2d = true;                           // fused 2-D-patch sepconv for the K <= 256, N <= 256 entry-flow layers (BQ_SEP2D=off)
   bool dw_cc32 = false;                        // 32-channel depthwise blocks (more blocks per SM) for C % 64 == 0 layers
   bool sep_fused = false;                      // experiment: fused depthwise->pointwise kernel for the 728->728 layers (BQ_SEPCONV=fused)
@@ -324,7 +326,7 @@ void kprofile_collect(bq_model* m) {
 }
 
 int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                const CUtensorMap& tr, int blk_k, const CUtensorMap* tb_half = nullptr) {
+                const CUtensorMap& tr, int blk_k, const CUtensorMap* tb_half = nullptr, const CUtensorMap* tb_q = nullptr) {
   bq_ctx* ctx = m->ctx;
   if (gp.M <= 0) return BQ_OK;
   if (m->use_simt) {
@@ -347,12 +349,21 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
     const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
     int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
     // a deeper operand ring where no residual staging is needed (the ring is what hides the DRAM round trip of A)
-    if (gp.residual)
-      gemm_tcgen05_2cta_kernel<k2Stages><<<2 * clusters, k2Threads, SmemPlan2<k2Stages>::kTotal, ctx->stream>>>(
-          ta, *tb_half, tc, tr, gp);
-    else
-      gemm_tcgen05_2cta_kernel<k2Stages + 1><<<2 * clusters, k2Threads, SmemPlan2<k2Stages + 1>::kTotalNoRes, ctx->stream>>>(
-          ta, *tb_half, tc, tr, gp);
+    if (gp.residual) {
+      gemm_tcgen05_2cta_kernel<k2Stages, false><<<2 * clusters, k2Threads, SmemPlan2<k2Stages>::kTotal, ctx->stream>>>(
+          ta, *tb_half, *tb_half, tc, tr, gp);
+    } else if (m->gemm_wide && tb_q && gp.bn_box == 256 && gp.N > 640 && gp.N <= 2 * k2WideN) {
+      // 728-wide pointwise convs: two 256 x 384 pair tiles per M tile instead of three 256 x 256 ones
+      GemmParams gw = gp;
+      gw.bn_box = k2WideN;
+      const int wide_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * 2;
+      const int wc = wide_tiles < ctx->num_sms / 2 ? wide_tiles : ctx->num_sms / 2;
+      gemm_tcgen05_2cta_kernel<k2Stages, true><<<2 * wc, k2Threads, SmemPlan2<k2Stages, true>::kTotalNoRes, ctx->stream>>>(
+          ta, *tb_half, *tb_q, tc, tr, gw);
+    } else {
+      gemm_tcgen05_2cta_kernel<k2Stages + 1, false><<<2 * clusters, k2Threads, SmemPlan2<k2Stages + 1>::kTotalNoRes, ctx->stream>>>(
+          ta, *tb_half, *tb_half, tc, tr, gp);
+    }
   } else if (m->gemm_direct_epi) {
     gemm_tcgen05_kernel<64, false><<<grid, kThreads, SmemPlan<64, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else {
@@ -396,6 +407,7 @@ int make_gemm(bq_model* m, Op& op, const bf16* a, int rows_per_tile, const PwWei
   op.tr = op.tc;
   if (residual && (rc = make_tmap(m->ctx, &op.tr, residual, (uint64_t)g.M, (uint64_t)w.cout, (uint64_t)w.cout, 128, 64))) return rc;
   if ((rc = make_tmap(m->ctx, &op.tb2, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, g.bn_box / 2, 64))) return rc;
+  if ((rc = make_tmap(m->ctx, &op.tb3, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, 64, 64))) return rc;
   return BQ_OK;
 }
 
@@ -444,7 +456,7 @@ int build_plan(bq_model* m) {
     g.b_ptr = (const bf16*)m->conv2.w.p; g.ldb = 288;
     if ((rc = make_tmap(ctx, &op.ta, A.p(0), (uint64_t)s1 * s1 * B, 32, 32, 128, 32))) return rc;
     if ((rc = make_tmap(ctx, &op.tb, m->conv2.w.p, 64, 288, 288, 64, 32))) return rc;
-    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb;      // unused by the direct-store epilogue
+    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb; op.tb3 = op.tb;      // unused by the direct-store epilogue
     op.Ho = s2; op.Wo = s2; op.Cout = 64;
     m->plan.push_back(op);
   }
@@ -594,7 +606,7 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       const double kin = g.conv_mode ? g.K / 9 : g.K;
       KScope ks(m, g.conv_mode ? BQ_K_GEMM_CONV2 : BQ_K_GEMM_PW, 2.0 * rows_out * g.N * g.K,
                 act * ((double)g.M * kin + rows_out * g.N * (g.residual ? 2 : 1) + (double)g.N * g.K));
-      return launch_gemm(m, g, op.ta, op.tb, op.tc, op.tr, op.blk_k, g.conv_mode ? nullptr : &op.tb2);
+      return launch_gemm(m, g, op.ta, op.tb, op.tc, op.tr, op.blk_k, g.conv_mode ? nullptr : &op.tb2, g.conv_mode ? nullptr : &op.tb3);
     }
     case OP_DW: {
       KScope ks(m, BQ_K_DW, 2.0 * 9 * nb * op.H * op.W * op.C, 2 * act * nb * op.H * op.W * op.C);
@@ -911,10 +923,14 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
   m->gemm_direct_epi = g && strcmp(g, "direct") == 0;   // debug switch: per-thread global stores in the epilogue
   m->gemm_2cta = !(g && (strcmp(g, "1cta") == 0 || strcmp(g, "direct") == 0));   // default: cta_group::2 pairs
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::sm100::SmemPlan2<bq::sm100::k2Stages>::kTotal);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages + 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        bq::sm100::SmemPlan2<bq::sm100::k2Stages + 1>::kTotalNoRes);
+  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       bq::sm100::SmemPlan2<bq::sm100::k2Stages, true>::kTotalNoRes);
+  const char* gw = getenv("BQ_GEMM_WIDE");
+  m->gemm_wide = gw && strcmp(gw, "on") == 0;
   const char* hv = getenv("BQ_HEAD");
   m->head_fused = !(hv && strcmp(hv, "unfused") == 0) &&   // debug switch: three-kernel head (expand / GEMM / final)
                   cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
