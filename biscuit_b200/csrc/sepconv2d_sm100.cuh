@@ -31,11 +31,14 @@ constexpr int kMaxPStages = 5, kAStages = 2, kBStages = 2;
 constexpr int kOffPatch = 0;
 // runtime layout (all offsets multiples of 1024): [patch x P][A x 2][B x 2 (N*128 B each)][out x 2][scale/shift][barriers]
 // P = 4 halo-patch stages for N = 256, 5 for N <= 128: the kernel is HBM-latency bound, so every spare KB is patch in flight
-__host__ __device__ inline int patch_stages(int N) { return N > 128 ? 4 : 5; }
+__host__ __device__ inline int patch_stages(int N) { (void)N; return 4; }
+// N == 128 ("dual" epilogue): the two 64-column halves of an item are drained CONCURRENTLY by the two groups of four
+// epilogue warps, each with its own pair of staging buffers, its own 128-thread barrier and its own TMA stores
+__host__ __device__ inline int out_bufs(int N) { return N == 128 ? 4 : 2; }
 __host__ __device__ inline int off_a(int N) { return patch_stages(N) * kPatchBytes; }
 __host__ __device__ inline int off_b(int N) { return off_a(N) + kAStages * kABytes; }
 __host__ __device__ inline int off_out(int N) { return off_b(N) + kBStages * N * 128; }
-__host__ __device__ inline int off_scale(int N) { return off_out(N) + 2 * kOutBytes; }
+__host__ __device__ inline int off_scale(int N) { return off_out(N) + out_bufs(N) * kOutBytes; }
 __host__ __device__ inline int off_bar(int N) { return off_scale(N) + 2 * 256 * 4; }
 __host__ __device__ inline int smem_bytes(int N) { return off_bar(N) + 512 + 1024; }
 constexpr int kThreads = 576;                                 // warp 0 TMA, 1 MMA, 2-9 epilogue (8), 10-17 producers (8)
@@ -159,6 +162,65 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
     const int row = quad * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
     int cs = 0; uint32_t cph = 0, cc = 0;
+    if (p.N == 128) {
+      // ---- dual epilogue: warps 2-5 own columns 0..63, warps 6-9 columns 64..127 of every item.  These layers have
+      // one or two k-blocks per item, the epilogue is their critical role (ncu: its warps busy 83 % of the time), and
+      // draining the halves one after the other cost four 256-thread barriers per item.
+      const bool hleader = (quad == 0 && lane == 0);              // warp 4 (half 0) / warp 8 (half 1)... quad 0 of each half
+      uint32_t item = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
+        const int img = it / per_img, t = it - img * per_img;
+        const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
+        const uint32_t buf = (item & 1u) * 2u + (uint32_t)half;
+        uint8_t* st = smem_gen + kOffOut + buf * kOutBytes;
+        mbar_wait(acc_full(cs), cph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * 256 + half * 64);
+        if (hleader) tma_store_wait_read1();                      // this half's store of two items ago has drained
+        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + (uint32_t)(g2 * 32), v);
+          tmem_ld_wait();
+          if (g2 == 1) {                                          // accumulators fully read -> next item may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(cs));
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = half * 64 + g2 * 32 + g * 8;
+            const float4 s0 = *(const float4*)(s_scale + n), s1 = *(const float4*)(s_scale + n + 4);
+            const float4 h0 = *(const float4*)(s_shift + n), h1 = *(const float4*)(s_shift + n + 4);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
+              if (p.relu_out) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o;
+            __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            const int chunk16 = g2 * 4 + g;
+            *(uint4*)(st + (size_t)row * 128 + ((chunk16 ^ (row & 7)) << 4)) = o;
+          }
+        }
+        fence_async_smem();
+        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (hleader) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"((uint64_t)&tmap_out), "r"(smem_base + kOffOut + buf * kOutBytes), "r"(half * 64), "r"(x0), "r"(y0), "r"(img)
+                       : "memory");
+          tma_store_commit();
+        }
+        if (++cs == 2) { cs = 0; cph ^= 1u; }
+      }
+      if (hleader) tma_store_wait_all();
+    } else
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int img = it / per_img, t = it - img * per_img;
       const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
