@@ -85,6 +85,9 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
   const int n_items = p.n_img * per_img;
   const int num_kb = p.K / 64;
   const uint32_t b_bytes = (uint32_t)p.N * 128u;
+  // K = 64 / 128 (one / two k-blocks per item): stage s of the B ring always holds k-block s % num_kb, so the weights
+  // are loaded once per CTA instead of once per item (16 KB of the 39 KB an item used to pull through TMA)
+  const bool b_resident = num_kb <= kBStages;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -110,6 +113,12 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
     if (lane == 0) {
       int ps = 0; uint32_t pph = 0;
       int bs = 0; uint32_t bph = 0;
+      if (b_resident) {                                          // K <= 128: the whole weight matrix fits the two B stages
+        for (int st = 0; st < kBStages; ++st) {
+          mbar_expect_tx(b_full(st), b_bytes);
+          tma_load_2d(smem_base + kOffB + st * kBBytes, &tmap_w, b_full(st), (st % num_kb) * 64, 0);
+        }
+      }
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int img = it / per_img, t = it - img * per_img;
         const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
@@ -122,6 +131,7 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
                 "r"(x0 - 1), "r"(y0 - 1), "r"(img)
               : "memory");
           if (++ps == kPStages) { ps = 0; pph ^= 1u; }
+          if (b_resident) continue;                              // weights were loaded once, above
           mbar_wait(b_empty(bs), bph ^ 1u);
           mbar_expect_tx(b_full(bs), b_bytes);
           tma_load_2d(smem_base + kOffB + bs * kBBytes, &tmap_w, b_full(bs), kb * 64, 0);
@@ -135,20 +145,22 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
       const uint32_t idesc = make_idesc(128, p.N);
       int as = 0; uint32_t aph = 0;                // A / B rings advance together (one step per k-block)
       int cs = 0; uint32_t cph = 0;                // accumulator stage per item
+      int gk = 0;                                  // k-blocks issued so far (resident weights: only the first two wait for B)
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         mbar_wait(acc_empty(cs), cph ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(cs * 256);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(a_full(as), aph);
-          mbar_wait(b_full(as), aph);
+          if (!b_resident || gk < kBStages) mbar_wait(b_full(as), aph);
+          ++gk;
           tc_fence_after();
           const uint64_t da = make_smem_desc<128>(smem_base + kOffA + as * kABytes);
           const uint64_t db = make_smem_desc<128>(smem_base + kOffB + as * kBBytes);
           for (int k = 0; k < 4; ++k)
             umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           umma_commit(a_empty(as));
-          umma_commit(b_empty(as));
+          if (!b_resident) umma_commit(b_empty(as));
           if (kb == num_kb - 1) umma_commit(acc_full(cs));
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
