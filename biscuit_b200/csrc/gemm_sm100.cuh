@@ -811,7 +811,10 @@ constexpr int kC2BBytes = 9 * 64 * 64;                   // 36 KB: nine taps x [
 constexpr int kC2AccStages = 4;
 constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + 256 + 1024;
 
-constexpr int kC2Threads = kThreads + 32;        // + a second MMA-issuing warp (small MMAs are issue-latency bound)
+// warp 0 TMA, warps 1 and 6 MMA issue (small MMAs are issue-latency bound), warps 2-5 and 7-10 epilogue: two warps per TMEM
+// lane quadrant, 32 of the 64 output columns each (with one warp per quadrant the epilogue -- ~2700 cycles per 128-row
+// tile against 576 tensor-pipe cycles -- was the critical role)
+constexpr int kC2Threads = 11 * 32;
 static __global__ void __launch_bounds__(kC2Threads, 1)
 conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [128 x 32] SW64*/,
                   const __grid_constant__ CUtensorMap tmap_b /*[64, 288] box [64 x 32] SW64*/, const GemmParams p) {
@@ -835,7 +838,7 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kC2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < kC2AccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < kC2AccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -891,8 +894,9 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
         umma_commit(tfull_bar(as));
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    const int quad = warp & 3;
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+    const int quad = warp & 3;                     // TMEM lanes a warp may read: 32 * (warp % 4)
+    const int half = warp >= 7 ? 1 : 0;            // columns [32 * half, +32)
     int as = 0; uint32_t aph = 0;
     // per-channel BN constants (64 channels) in registers-by-load: read once
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -907,24 +911,20 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
       }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      uint32_t v[64];
-      {
-        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 64);
-        tmem_ld_32x32b_x32(taddr, v0);
-        tmem_ld_32x32b_x32(taddr + 32u, v1);
-        tmem_ld_wait();
-      }
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 64 + half * 32), v);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (row_ok) {
-        __nv_bfloat16* optr = p.out + orow * p.ldc;
+        __nv_bfloat16* optr = p.out + orow * p.ldc + half * 32;
+        const float* scp = p.scale + half * 32;
+        const float* shp = p.shift + half * 32;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 s0 = __ldg((const float4*)(p.scale + g * 8)), s1 = __ldg((const float4*)(p.scale + g * 8 + 4));
-          const float4 h0 = __ldg((const float4*)(p.shift + g * 8)), h1 = __ldg((const float4*)(p.shift + g * 8 + 4));
+        for (int g = 0; g < 4; ++g) {
+          const float4 s0 = __ldg((const float4*)(scp + g * 8)), s1 = __ldg((const float4*)(scp + g * 8 + 4));
+          const float4 h0 = __ldg((const float4*)(shp + g * 8)), h1 = __ldg((const float4*)(shp + g * 8 + 4));
           const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
           const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           float f[8];
