@@ -76,6 +76,10 @@ SIGNATURES = {
     "bq_stain_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "bq_model_set_normalizer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bq_bootstrap_confusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p]),
+    "bq_delong_placements": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "bq_model_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bq_model_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bq_debug_umma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

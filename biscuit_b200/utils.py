@@ -165,3 +165,66 @@ def slides_from_model_manifest(model_path, dataset=None):
                 rows = list(csv.DictReader(f))
             return [r["slide"] for r in rows if dataset is None or r.get("dataset") == dataset]
     raise OSError(f"Could not find slide manifest for model {model_path}")
+
+
+# --- evaluation metrics ------------------------------------------------------
+
+def prediction_metrics(y_true, y_pred, threshold):
+    """AUC confidence interval (DeLong), accuracy, sensitivity / specificity and Youden's J with its
+    bootstrap confidence interval (reference utils.py:400-464).
+
+    The 500 bootstrap samples of 150 rows are drawn with the same ``np.random.choice`` calls as the
+    reference (so a seeded ``np.random`` gives the reference's numbers); their confusion matrices and the
+    DeLong placement values are computed on the GPU, the order-sensitive finish (``statistics.mean`` /
+    ``variance``, ``np.cov``, ``scipy.stats.norm``) by the same library calls as the reference."""
+    import ctypes as C
+    from statistics import mean, variance
+
+    from scipy import stats
+
+    from . import _ffi
+    from .delong import delong_roc_variance
+
+    yt = y_true.astype(bool)
+    yp = y_pred > threshold
+    alpha = 0.05
+    z = stats.norm.ppf((1 - alpha / 2))
+    tp = np.logical_and(yt, yp).sum()
+    fp = np.logical_and(np.logical_not(yt), yp).sum()
+    tn = np.logical_and(np.logical_not(yt), np.logical_not(yp)).sum()
+    fn = np.logical_and(yt, np.logical_not(yp)).sum()
+    acc = (tp + tn) / (tp + tn + fp + fn)
+    sensitivity = tp / (tp + fn)
+    specificity = tn / (tn + fp)
+
+    n_boot, n_samp = 500, 150                                         # utils.py:430-431
+    idx = np.empty((n_boot, n_samp), np.int64)
+    population = np.arange(yt.shape[0])
+    for b in range(n_boot):                                           # same RNG consumption as the reference
+        idx[b] = np.random.choice(population, size=(n_samp,))
+    ctx = _ffi.default_context()
+    counts = np.empty((n_boot, 4), np.int64)
+    yt8 = np.ascontiguousarray(yt, dtype=np.uint8)
+    yp8 = np.ascontiguousarray(yp, dtype=np.uint8)
+    _ffi.check(ctx.handle, ctx.lib.bq_bootstrap_confusion(ctx.handle, _ffi.ptr(yt8), _ffi.ptr(yp8), int(yt.shape[0]),
+                                                          _ffi.ptr(idx), C.c_int32(n_boot), C.c_int32(n_samp),
+                                                          _ffi.ptr(counts)), "bq_bootstrap_confusion")
+    _tp, _fp, _tn, _fn = counts[:, 0], counts[:, 1], counts[:, 2], counts[:, 3]
+    all_jac = (((_tn + 0.5 * z**2) / (_tn + _fp + z**2)) - ((_fn + 0.5 * z**2) / (_fn + _tp + z**2)))   # utils.py:438-439
+    all_jac = list(all_jac)
+    jac = mean(all_jac)
+    jac_var = variance(all_jac)
+    jac_low = jac - z * np.sqrt(jac_var)
+    jac_high = jac + z * np.sqrt(jac_var)
+
+    if not np.array_equal(np.unique(y_true), [0, 1]):                 # utils.py:448-450
+        log.warning("Unable to calculate CI; NaNs exist")
+        ci = [None, None]
+    else:
+        delong_auc, auc_cov = delong_roc_variance(y_true, y_pred)
+        auc_std = np.sqrt(auc_cov)
+        lower_upper_q = np.abs(np.array([0, 1]) - alpha / 2)
+        ci = stats.norm.ppf(lower_upper_q, loc=delong_auc, scale=auc_std)
+        ci[ci > 1] = 1
+    return {"auc_low": ci[0], "auc_high": ci[1], "acc": acc, "sens": sensitivity, "spec": specificity,
+            "youden": sensitivity + specificity - 1, "youden_low": jac_low, "youden_high": jac_high}

@@ -200,6 +200,20 @@ int bq_stain_normalize(bq_ctx* ctx, int32_t kind, const uint8_t* tiles, int64_t 
 /* Make bq_predict_uq normalise every tile first (kind = BQ_NORM_NONE switches it off again). */
 int bq_model_set_normalizer(bq_model* m, int32_t kind, const float target_means[3], const float target_stds[3]);
 
+/* ------------------------------------------------------------------------------------------------
+ * evaluation metrics next to the path
+ *   replaces the bootstrap loop of utils.prediction_metrics (biscuit/utils.py:428-440) and the midrank
+ *   passes of delong.fastDeLong (biscuit/delong.py:60-69); the order-sensitive floating-point finish
+ *   (np.cov, statistics.mean / variance, scipy.stats.norm) stays in the Python wrapper
+ * ---------------------------------------------------------------------------------------------- */
+/* counts[b] = {tp, fp, tn, fn} of the n_samp rows idx[b][0..n_samp) (uint8 y_true / thresholded y_pred, length n) */
+int bq_bootstrap_confusion(bq_ctx* ctx, const uint8_t* y_true, const uint8_t* y_pred_bin, int64_t n,
+                           const int64_t* idx, int32_t n_boot, int32_t n_samp, int64_t* counts);
+/* v[i] = V01 placement value of a positive / V10 of a negative example (original order, float64);
+ * tz_pos_sum = sum of the positives' midranks among all examples; n_pos = number of positives.  n <= 2^20. */
+int bq_delong_placements(bq_ctx* ctx, const void* score, int32_t dtype, const uint8_t* label, int64_t n,
+                         double* v, double* tz_pos_sum, int64_t* n_pos);
+
 /* Developer hook (hardware probe, not on the product path): one 128x16x16 tcgen05.mma whose A operand starts `shift`
  * rows into a 128B-swizzled [rows x 64] bf16 tile, channel group cg, against an identity B in the no-swizzle layout;
  * base_offset_mode 1 sets the descriptor base_offset field to (addr >> 7) & 7.  out = float [128][16]. */
