@@ -209,7 +209,7 @@ depthwise3x3_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[
 }
 
 // ---------------------------------------------------------------------------------------------------
-// depthwise 3x3 (production kernel): shared-memory staged, register sliding window.
+// depthwise 3x3, second generation (BQ_DW=v2; superseded by dwpipe_sm100.cuh): shared-memory staged, register sliding window.
 // One block = (image, 19x19 pixel tile, chunk of CC channels).  The (TH+2)x(TW+2) halo tile is loaded ONCE with
 // 16-byte coalesced loads (4 in flight per thread; optional ReLU applied here, once per element).  A thread
 // owns (4 channels, one tile column) and walks DOWN the column keeping the 3x3 window in registers: per 4
