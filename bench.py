@@ -345,7 +345,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     out = run_native_arm(args, rank, world, local_rank)
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world > 1:
+        # the CPU baseline is a rank-0, N = 1 measurement (torchrun pins OMP_NUM_THREADS=1 and the other ranks would
+        # spin in a barrier for its duration): not repeated on the multi-GPU lines
+        out["cpu_baseline"] = {"value": None, "unit": "tiles/s", "cores": 0, "kind": "port",
+                               "sample": "not measured at N > 1 (rank-0, N = 1 measurement: see the N = 1 line)"}
+    elif rank == 0 and not args.no_cpu_baseline:
         oracle, threads = make_cpu_oracle()
         probe = cpu_sample_tiles(1)
         t0 = time.perf_counter()

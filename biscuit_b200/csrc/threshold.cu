@@ -125,6 +125,8 @@ __device__ __forceinline__ void kahan_step(T& s, T& c, T v) {
 
 // One warp per group: lanes fetch 32 rows coalesced (next chunk prefetched), then the warp replays the
 // kept rows strictly in row order; every lane runs the same two Kahan chains (y_pred, uncertainty).
+// NaN entries are skipped PER COLUMN with their own observation count, as pandas' group_mean does (a NaN
+// uncertainty can only reach this kernel when the tile filter is off; NaN y_pred is rejected upstream).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 group_kahan_kernel(const T* __restrict__ yp, const T* __restrict__ unc, const uint8_t* __restrict__ yt,
@@ -138,7 +140,7 @@ group_kahan_kernel(const T* __restrict__ yp, const T* __restrict__ unc, const ui
        g += gridDim.x * warps_per_block) {
     const int64_t b = seg_begin[g], e = seg_end[g];
     T sp = 0, cp = 0, su = 0, cu = 0;
-    int64_t cnt = 0, ysum = 0, first = -1;
+    int64_t cnt = 0, cnt_p = 0, cnt_u = 0, ysum = 0, first = -1;
     // prefetch chunk 0
     int64_t r = b + lane;
     bool valid = r < e;
@@ -158,7 +160,11 @@ group_kahan_kernel(const T* __restrict__ yp, const T* __restrict__ unc, const ui
       bool keep = valid && (!filter_on || (double)u < tile_uq);
       unsigned m = __ballot_sync(0xffffffffu, keep);
       unsigned my = __ballot_sync(0xffffffffu, keep && y);
+      const unsigned mp = __ballot_sync(0xffffffffu, keep && p == p);
+      const unsigned mu = __ballot_sync(0xffffffffu, keep && u == u);
       cnt += __popc(m);
+      cnt_p += __popc(mp);
+      cnt_u += __popc(mu);
       ysum += __popc(my);
       if (first < 0 && m) first = __shfl_sync(0xffffffffu, row, __ffs(m) - 1);
       while (m) {
@@ -166,15 +172,15 @@ group_kahan_kernel(const T* __restrict__ yp, const T* __restrict__ unc, const ui
         m &= m - 1;
         T pv = __shfl_sync(0xffffffffu, p, k);
         T uv = __shfl_sync(0xffffffffu, u, k);
-        kahan_step(sp, cp, pv);
-        kahan_step(su, cu, uv);
+        if ((mp >> k) & 1u) kahan_step(sp, cp, pv);
+        if ((mu >> k) & 1u) kahan_step(su, cu, uv);
       }
       valid = valid2; row = row2; p = p2; u = u2; y = y2;
     }
     if (lane == 0) {
       if (cnt > 0) {
-        g_pred[g] = div_rn(sp, (T)cnt);
-        g_unc[g] = div_rn(su, (T)cnt);
+        g_pred[g] = cnt_p > 0 ? div_rn(sp, (T)cnt_p) : (T)NAN;
+        g_unc[g] = cnt_u > 0 ? div_rn(su, (T)cnt_u) : (T)NAN;
         g_true[g] = __ddiv_rn((double)ysum, (double)cnt);
       } else {
         g_pred[g] = (T)NAN;

@@ -203,7 +203,8 @@ def _open_table(df, ctx=None) -> _DeviceTable:
 
 def _tile_stage(tab: _DeviceTable, df, pred_thresh, patients):
     """threshold.py:140-177 on an open device table; mutates df; returns pred_thresh used."""
-    n_nan, n_nonfinite, _, n_badlabel = tab.validate()
+    n_nan, n_nonfinite, n_unc_nonfinite, n_badlabel = tab.validate()
+    tab.n_unc_nonfinite = int(n_unc_nonfinite)      # sklearn's check fires only where the uncertainty feeds a ROC
     if n_nan:                                                         # :141-142
         raise errors.PredsContainNaNError
     if n_nonfinite:
@@ -508,6 +509,8 @@ def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pr
             log.debug("Not performing tile-level uncertainty thresholding.")
             tile_uq, tile_uq_eff = None, None
         else:                                                         # :416-426
+            if getattr(tab, "n_unc_nonfinite", 0):                     # roc_curve -> assert_all_finite (uncaught at :419)
+                raise ValueError("Input contains NaN or infinity.")
             r = tab.tile_roc(_ffi.SCORE_UNCERTAINTY, _ffi.LABEL_INCORRECT)
             tile_uq = _youden_or_raise(r)
             log.debug(f"Tile-level optimal UQ threshold: {tile_uq:.4f}")

@@ -37,10 +37,11 @@ import torch.nn.functional as F
 BN_EPS = 1e-3
 TILE_PX = 299
 
-# The layer table and the random-init weight generator are plain data helpers shared with the product
-# (bench.py must not import oracle/ on its GPU path); the ALGORITHM restated below is independent of them.
-from biscuit_b200.weights import (ENTRY_BLOCKS, FEATURES, MIDDLE_BLOCKS, layer_table,  # noqa: E402,F401
-                                  random_init as make_weights)
+# The layer list and the random-init generator are the ORACLE'S OWN statement (oracle/xception_arch.py), independent of
+# biscuit_b200.weights; tests/test_model_oracle_cpu.py checks that the two statements agree and anchors this one on
+# Keras' published parameter count.
+from oracle.xception_arch import (ENTRY_BLOCKS, FEATURES, MIDDLE_BLOCKS, layer_table,  # noqa: E402,F401
+                                  make_weights)
 
 
 # ----------------------------------------------------------------------------------------

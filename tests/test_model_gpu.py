@@ -272,3 +272,104 @@ def test_results_do_not_depend_on_micro_batch():
     for a, b, name in zip(outs[0], outs[1], ("mean", "std", "features")):
         bad = np.nonzero(np.abs(a - b).reshape(n, -1).max(1) > 0)[0]
         assert a.tobytes() == b.tobytes(), f"{name}: {len(bad)} tiles depend on the micro-batch size, first {bad[:8]}"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The configuration bench.py times (max_batch = 512: CUDA-graph replay, batched fused head, full-size GEMM rings)
+# tied to the oracle
+# ----------------------------------------------------------------------------------------------------------------
+BENCH_BATCH = 512
+
+
+@pytest.fixture(scope="module")
+def bench_iface(weights):
+    from biscuit_b200.uq import UncertaintyInterface
+    it = UncertaintyInterface(weights, max_batch=BENCH_BATCH)
+    yield it
+    it.close()
+
+
+def test_bench_micro_batch_bit_identical_to_small_batch(weights, bench_iface, iface):
+    """530 tiles at max_batch = 512 (one full graph-replayed micro-batch + a partial one, fused head launched on
+    >= 592-tile... here 530-tile batches) and the same tiles at max_batch = 4 (the batch size the stage-wise oracle
+    parity tests run at): bit-identical features / mean / std.  Transitively ties the bench configuration to the
+    oracle."""
+    import torch
+    n = 530
+    base = synth.tiles_u8(53, seed=9, n_slides=4)
+    t = torch.from_numpy(base).cuda().repeat(10, 1, 1, 1).contiguous()
+    big = bench_iface.predict(t, T=T, seed=21, return_features=True)
+    small = iface.predict(t, T=T, seed=21, return_features=True)
+    for a, b, name in zip(big, small, ("mean", "std", "features")):
+        bad = np.nonzero(np.abs(a - b).reshape(n, -1).max(1) > 0)[0]
+        assert a.tobytes() == b.tobytes(), f"{name}: {len(bad)} tiles differ between max_batch 512 and 4, first {bad[:8]}"
+    # a second call replays the captured graph: still identical
+    again = bench_iface.predict(t, T=T, seed=21, return_features=True)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(big, again))
+
+
+def test_oracle_parity_at_bench_micro_batch(weights, bench_iface, tiles):
+    """max_batch = 512: the six oracle tiles scattered over a 520-tile run (first / interior / last row of the full
+    micro-batch, and the partial second micro-batch) against the bf16-emulated oracle directly, own Philox stream
+    addressed by the GLOBAL tile index."""
+    n = 520
+    pos = [0, 63, 257, 511, 512, 519]
+    filler = synth.tiles_u8(16, seed=33, n_slides=2)
+    allt = np.concatenate([filler] * (n // 16 + 1))[:n].copy()
+    for k, p in enumerate(pos):
+        allt[p] = tiles[k]
+    mean, std, feats = bench_iface.predict(allt, T=T, seed=SEED, return_features=True)
+    o = X.XceptionUQOracle(weights, emulate_bf16=True)
+    for k, p in enumerate(pos):
+        m_ref, s_ref, f_ref = o.predict_uq(tiles[k:k + 1], T=T, seed=SEED, tile_index_base=p, return_features=True)
+        assert np.abs(feats[p] - f_ref[0]).max() <= 3e-2 * np.abs(f_ref).max(), (p, np.abs(feats[p] - f_ref[0]).max())
+        assert np.abs(mean[p] - m_ref[0]).max() <= 4e-3, (p, mean[p], m_ref[0])
+        assert np.abs(std[p] - s_ref[0]).max() <= 4e-3, (p, std[p], s_ref[0])
+
+
+def test_config1_end_to_end_512_tiles_4_slides(weights, bench_iface):
+    """BASELINE.json configs[0] / SURVEY.md 8d config 1: 512 synthetic tiles = 4 slides x 128 (per-slide colour
+    bias), labels slides 0,1 -> 0 and 2,3 -> 1, T = 30 -> `predict_table` -> `threshold.apply(tile_uq = q50 of the
+    tile uncertainty, slide_uq = q75 of the slide uncertainty, tile_pred = slide_pred = .5)`.
+    Model: per-tile mean / std within 4e-3 of the CPU restatement (bf16-emulated tier, one backbone pass -- identical to
+    the reference schedule of T full passes, test_reference_schedule_equivalence).  Thresholding: include / exclude
+    decisions, slide table and metrics BIT-equal to the oracle's `apply` on the GPU's own tile table."""
+    import pandas as pd
+    from biscuit_b200 import threshold
+    from biscuit_b200.uq import predict_table
+    from oracle import threshold_oracle as O
+    from helpers import assert_same_df, assert_same_results
+    n, n_slides = 512, 4
+    t = synth.tiles_u8(n, seed=0, n_slides=n_slides)
+    slides = np.repeat([f"slide{j}" for j in range(n_slides)], n // n_slides)
+    y_true = np.repeat([0, 0, 1, 1], n // n_slides).astype(np.int64)
+    df = predict_table(bench_iface, t, slides, y_true, T=T, seed=SEED)
+    assert list(df.columns) == ["slide", "y_true", "y_pred", "uncertainty"] and len(df) == n
+    assert df["y_pred"].dtype == np.float32 and df["uncertainty"].dtype == np.float32
+    # model half vs the CPU restatement
+    o = X.XceptionUQOracle(weights, emulate_bf16=True)
+    m_ref, s_ref = o.predict_uq(t, T=T, seed=SEED)
+    d_mean = np.abs(df["y_pred"].to_numpy() - m_ref[:, 1]).max()
+    d_std = np.abs(df["uncertainty"].to_numpy() - s_ref[:, 1]).max()
+    print("config 1: d_mean", d_mean, "d_std", d_std)
+    assert d_mean <= 4e-3 and d_std <= 4e-3
+    # thresholding half, bit-exact on the GPU's own table
+    tile_uq = np.float64(np.quantile(df["uncertainty"].to_numpy().astype(np.float64), 0.5))
+    slide_unc = df.groupby("slide", sort=False)["uncertainty"].mean().to_numpy().astype(np.float64)
+    slide_uq = np.float64(np.quantile(slide_unc, 0.75))
+    for level, keep in (("slide", "high_confidence"), ("slide", "low_confidence")):
+        kw = dict(tile_uq=tile_uq, slide_uq=slide_uq, tile_pred=0.5, slide_pred=0.5, keep=keep, level=level)
+        a, b = df.copy(), df.copy()
+        r_ref, s_ref_df = O.apply(a, **kw)
+        r_gpu, s_gpu_df = threshold.apply(b, **kw)
+        assert_same_results(r_ref, r_gpu, f"config1 {keep}")
+        assert_same_df(s_ref_df, s_gpu_df, f"config1 {keep}")
+        assert_same_df(a, b, f"config1 mutated tile table {keep}")
+    # the decisions also agree with thresholding the ORACLE's predictions wherever no value sits within tolerance of a cut
+    ref_tab = pd.DataFrame({"slide": slides, "y_true": y_true, "y_pred": m_ref[:, 1], "uncertainty": s_ref[:, 1]})
+    r2, s2 = O.apply(ref_tab, tile_uq=tile_uq, slide_uq=slide_uq, tile_pred=0.5, slide_pred=0.5)
+    r1, s1 = threshold.apply(df.copy(), tile_uq=tile_uq, slide_uq=slide_uq, tile_pred=0.5, slide_pred=0.5)
+    if s1 is not None and s2 is not None:
+        far = np.abs(s2["uncertainty"].to_numpy().astype(np.float64) - slide_uq) > 4e-3
+        common = [s for s in s2["slide"][far] if s in set(s1["slide"])]
+        assert len(common) == int(far.sum()), (list(s1["slide"]), list(s2["slide"]))
