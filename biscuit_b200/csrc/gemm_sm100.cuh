@@ -115,6 +115,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
+// One lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit take uniform-register operands: when they are issued from
+// inside an `if (lane == 0)` region every operand lives in a vector register and ptxas wraps each instruction in an
+// R2UR / ELECT / BRA.U.ANY loop (~25 instructions per MMA; ncu showed the single issuing thread, not L2, pacing the
+// GEMMs).  Issuing from warp-uniform control flow under elect.sync keeps descriptors and loop counters in uniform
+// registers: ~3 instructions per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+// warp index the compiler can prove warp-uniform (the shuffle is the hint, as in cutlass::canonical_warp_idx_sync)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -593,7 +606,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   volatile uint32_t* tmem_slot_ptr =
       (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + k2ResBufs));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool is_leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -655,8 +668,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: leader CTA, one thread =====================
-    if (is_leader && lane == 0) {
+    // ===================== MMA issuer: leader CTA; the whole warp walks the loop, one elected lane issues =====================
+    if (is_leader) {
+      if (tmem_base != 0u) __trap();             // all 512 columns are allocated: the base can only be 0
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -667,8 +681,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t idesc = make_idesc(2 * kBM, WIDE ? 256 : n_cols);
         const uint32_t idesc2 = make_idesc(2 * kBM, WIDE ? n_cols - 256 : 16);
         mbar_wait(tempty_bar(as), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
+        const uint32_t d_tmem = (uint32_t)(as * kBNMax);
+#pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
@@ -677,12 +691,25 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (kb == num_kb - 1) ksteps = (p.K - kb * BLOCK_K + 15) / 16;
           const uint64_t da = make_smem_desc<128>(a_src), db = make_smem_desc<128>(b_src);
           const uint64_t db2 = make_smem_desc<128>(b_src + Plan::kBBytes);
-          for (int k = 0; k < ksteps; ++k) {
-            umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-            if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + (uint64_t)(2 * k), db2 + (uint64_t)(2 * k), idesc2, (kb | k) ? 1u : 0u);
+          if (elect_one()) {
+            umma_bf16_2cta(d_tmem, da, db, idesc, kb ? 1u : 0u);
+            if (WIDE) umma_bf16_2cta(d_tmem + 256u, da, db2, idesc2, kb ? 1u : 0u);
+            if (ksteps > 1) {
+              umma_bf16_2cta(d_tmem, da + 2u, db + 2u, idesc, 1u);
+              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 2u, db2 + 2u, idesc2, 1u);
+            }
+            if (ksteps > 2) {
+              umma_bf16_2cta(d_tmem, da + 4u, db + 4u, idesc, 1u);
+              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 4u, db2 + 4u, idesc2, 1u);
+            }
+            if (ksteps > 3) {
+              umma_bf16_2cta(d_tmem, da + 6u, db + 6u, idesc, 1u);
+              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 6u, db2 + 6u, idesc2, 1u);
+            }
+            umma_commit_2cta(empty_bar(s));
+            if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(as));
           }
-          umma_commit_2cta(empty_bar(s));
-          if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(as));
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         if (++as == ACC) { as = 0; aph ^= 1u; }

@@ -20,6 +20,7 @@
 #include "dwpipe_sm100.cuh"
 #include "sepconv_sm100.cuh"
 #include "sepconv2d_sm100.cuh"
+#include "sepmid_sm100.cuh"
 #include "stain_sm100.cuh"
 
 int bq_stain_launch(bq_ctx* ctx, const uint8_t* tiles_dev, int64_t n, int32_t px, const float* lut_dev, float* stats_dev,
@@ -54,14 +55,15 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 K-major matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols]
 int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-              uint32_t box_rows, uint32_t box_cols) {
+              uint32_t box_rows, uint32_t box_cols, bool no_swizzle = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * sizeof(bf16)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle swz = box_cols * sizeof(bf16) == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  CUtensorMapSwizzle swz = no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                           : box_cols * sizeof(bf16) == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                            : box_cols * sizeof(bf16) == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                            : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -191,7 +193,7 @@ int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int 
 // ------------------------------------------------------------------------------------------------
 // execution plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED, OP_SEP2D };
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED, OP_SEP2D, OP_SEPMID, OP_PADCOPY };
 
 struct Op {
   OpKind kind;
@@ -207,6 +209,9 @@ struct Op {
   const bf16* bdiag = nullptr;
   bq::sepf::SepParams sp;     // OP_SEPFUSED
   bq::sep2d::Sep2dParams s2;  // OP_SEP2D
+  bq::sepmid::SepMidParams sm; // OP_SEPMID
+  int to_padded = 0;          // OP_PADCOPY direction
+  bool padded_out = false;    // the op's output is in the zero-padded 20 x 20 layout (debug-stage copies strip it)
   // gemm
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
@@ -243,6 +248,8 @@ struct bq_model {
   bool dw_cc32 = false;                        // 32-channel depthwise blocks (more blocks per SM) for C % 64 == 0 layers
   bool sep_fused = false;                      // experiment: fused depthwise->pointwise kernel for the 728->728 layers (BQ_SEPCONV=fused)
   bool conv2_is = true;                        // input-stationary block1_conv2 (BQ_CONV2=taps selects the per-tap reload kernel)
+  bool sep_mid = true;                         // fused depthwise->pointwise kernel on the zero-padded layout for the 728-wide middle flow (BQ_SEPMID=off)
+  DevBuf midbuf[4];                            // dedicated zero-bordered [max_batch * 400 (+ slack), 728] activation buffers of the middle flow
   int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
   int max_batch = 0;
   int px = 299;
@@ -548,6 +555,47 @@ int build_plan(bq_model* m) {
   };
   if ((rc = res_block(2, 128, 128, 0, 2)) || (rc = res_block(3, 256, 256, 1, 2)) || (rc = res_block(4, 728, 728, 1, 2))) return rc;
   // ---- middle flow: 8 x (3 x (ReLU, sepconv, BN)) + identity
+  if (m->sep_mid && H == bq::sepmid::kMap && C == bq::sepmid::kC) {
+    // Fused depthwise->pointwise kernel on the zero-padded flattened layout (sepmid_sm100.cuh).  The four buffers are
+    // dedicated to this layout: zeroed once here, and only VALID pixels are ever written, so the border stays zero.
+    using namespace bq::sepmid;
+    const uint64_t rows = (uint64_t)B * kImgRows + kSlackRows;
+    for (auto& b : m->midbuf) {
+      if ((rc = bq_alloc(ctx, b, rows * kC * sizeof(bf16)))) return rc;
+      BQ_CUDA(ctx, cudaMemset(b.p, 0, rows * kC * sizeof(bf16)));
+    }
+    auto P = [&](int i) { return (bf16*)m->midbuf[i].p; };
+    auto add_mid = [&](int src, int dst, int res, const SepWeights& sw, int relu_in, int relu_out, const char* tag) -> int {
+      Op op; op.kind = OP_SEPMID; op.stage = 3; op.padded_out = true;
+      if (tag) op.tag = tag;
+      op.in = P(src); op.out = P(dst); op.in2 = res >= 0 ? P(res) : nullptr;
+      op.H = kMap; op.W = kMap; op.C = kC; op.Ho = kMap; op.Wo = kMap; op.Cout = kC; op.relu_in = relu_in;
+      op.sm.n_rows = B * kImgRows; op.sm.relu_out = relu_out;
+      op.sm.dw = (const float*)sw.dw.p; op.sm.scale = (const float*)sw.pw.scale.p; op.sm.shift = (const float*)sw.pw.shift.p;
+      op.sm.residual = op.in2;
+      int r;
+      if ((r = make_tmap(ctx, &op.ta, P(src), rows, kC, kC, kWinRows, 64, true))) return r;
+      if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, kC, kC, kC, 128, 64))) return r;
+      if ((r = make_tmap(ctx, &op.tc, P(dst), rows, kC, kC, kMap, 64, true))) return r;
+      m->plan.push_back(op);
+      return BQ_OK;
+    };
+    { Op op; op.kind = OP_PADCOPY; op.stage = 3; op.in = A.p(X); op.out = P(0); op.to_padded = 1; op.padded_out = true;
+      op.H = kMap; op.W = kMap; op.C = kC; op.Ho = kMap; op.Wo = kMap; op.Cout = kC; m->plan.push_back(op); }
+    int x = 0;                                   // padded buffer holding the block input (= residual)
+    for (int b = 5; b <= 12; ++b) {
+      const std::string pre = "block" + std::to_string(b) + "_sepconv";
+      const SepWeights &w1 = *m->sep.at(pre + "1"), &w2 = *m->sep.at(pre + "2"), &w3 = *m->sep.at(pre + "3");
+      const std::string tag = "block" + std::to_string(b);
+      const int a = (x + 1) & 3, bb = (x + 2) & 3, c = (x + 3) & 3;
+      if ((rc = add_mid(x, a, -1, w1, 1, 1, nullptr))) return rc;
+      if ((rc = add_mid(a, bb, -1, w2, 0, 1, nullptr))) return rc;
+      if ((rc = add_mid(bb, c, x, w3, 0, 0, tag.c_str()))) return rc;
+      x = c;
+    }
+    { Op op; op.kind = OP_PADCOPY; op.stage = 3; op.in = P(x); op.out = A.p(X); op.to_padded = 0;
+      op.H = kMap; op.W = kMap; op.C = kC; op.Ho = kMap; op.Wo = kMap; op.Cout = kC; m->plan.push_back(op); }
+  } else
   for (int b = 5; b <= 12; ++b) {
     int t[4]; others(X, t);
     const std::string pre = "block" + std::to_string(b) + "_sepconv";
@@ -678,6 +726,24 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
         bq::sep2d::sepconv2d_fused_kernel<true><<<grid, bq::sep2d::kThreads, smem2d, ctx->stream>>>(op.ta, op.tb, op.tc, s2);
       else
         bq::sep2d::sepconv2d_fused_kernel<false><<<grid, bq::sep2d::kThreads, smem2d, ctx->stream>>>(op.ta, op.tb, op.tc, s2);
+      break;
+    }
+    case OP_SEPMID: {
+      bq::sepmid::SepMidParams sm = op.sm;
+      sm.n_rows = nb * bq::sepmid::kImgRows;
+      const int items = (sm.n_rows + bq::sepmid::kItemPx - 1) / bq::sepmid::kItemPx;
+      const int clusters = items < ctx->num_sms / 2 ? items : ctx->num_sms / 2;
+      const double px_n = (double)nb * op.H * op.W;
+      KScope ks(m, BQ_K_SEP_MID, 2.0 * px_n * op.C * (op.C + 9.0), act * px_n * op.C * (sm.residual ? 3.0 : 2.0));
+      if (op.relu_in)
+        bq::sepmid::sepconv_mid_kernel<true><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, sm);
+      else
+        bq::sepmid::sepconv_mid_kernel<false><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, sm);
+      break;
+    }
+    case OP_PADCOPY: {
+      KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.H * op.W * op.C);
+      bq::sepmid::pad_copy_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(op.in, op.out, nb, op.to_padded);
       break;
     }
     case OP_GAP: {
@@ -946,6 +1012,10 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->use_graph = !(gr && strcmp(gr, "off") == 0);
   const char* sf = getenv("BQ_SEPCONV");
   m->sep_fused = sf && strcmp(sf, "fused") == 0;
+  const char* smid = getenv("BQ_SEPMID");
+  m->sep_mid = !(smid && strcmp(smid, "off") == 0) && !m->sep_fused && !m->use_simt;
+  cudaFuncSetAttribute(bq::sepmid::sepconv_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepmid::kSmem);
+  cudaFuncSetAttribute(bq::sepmid::sepconv_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepmid::kSmem);
   cudaFuncSetAttribute(bq::sepf::sepconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepf::kSmem);
   const char* c2 = getenv("BQ_CONV2");
   m->conv2_is = !(c2 && strcmp(c2, "taps") == 0);
@@ -1222,6 +1292,14 @@ int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const cha
   if (total > out_capacity) return bq_fail(ctx, BQ_ERR_ARG, "output buffer too small: need %lld floats", (long long)total);
   void* scr = nullptr;
   if ((rc = bq_scratch(ctx, total * 4, &scr))) return rc;
+  if (op->padded_out) {
+    // zero-padded 20 x 20 layout -> dense [n, 19, 19, 728] behind the fp32 area of the scratch buffer
+    if ((rc = bq_scratch(ctx, total * 4 + total * 2 + 256, &scr))) return rc;
+    bf16* dense = (bf16*)((char*)scr + ((total * 4 + 255) / 256) * 256);
+    bq::sepmid::pad_copy_kernel<<<1024, 256, 0, ctx->stream>>>(src, dense, (int)n, 0);
+    BQ_LAUNCH_CHECK(ctx);
+    src = dense;
+  }
   bf16_to_f32_kernel<<<1024, 256, 0, ctx->stream>>>(src, (float*)scr, total);
   BQ_LAUNCH_CHECK(ctx);
   if ((rc = bq_from_device(ctx, out, scr, total * 4))) return rc;

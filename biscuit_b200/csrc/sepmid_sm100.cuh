@@ -1,0 +1,379 @@
+// Fused SeparableConv2D for the 728 -> 728 layers on the 19 x 19 maps (24 middle-flow layers + block13_sepconv1:
+// 56 % of the network's FLOPs).  The depthwise result never exists in HBM and nothing is computed twice:
+//
+//     out[p, n] = epilogue( sum_c  depthwise3x3(relu?(x))[p, c] * Wpw[n, c] )        (+ residual[p, n])
+//
+// Two ideas make it fit the machine.
+//
+// (1) ZERO-PADDED FLATTENED LAYOUT.  The activations of these layers live in dedicated buffers with one zero column
+//     and one zero row per image: pixel (y, x) of image b is row  b*400 + y*20 + x  of a [rows, 728] bf16 matrix, and
+//     rows with x == 19 or y == 19 are zero and are never written.  In that layout the 3 x 3 'same' depthwise is nine
+//     FIXED row offsets {-21,-20,-19,-1,0,+1,+19,+20,+21} with no border predicate anywhere (the neighbour of a border
+//     pixel is a zero row), the halo of ANY run of consecutive rows is one 2-D TMA box, and a work item need not align
+//     with an image.  Cost: 400 / 361 = 1.108 x the rows.
+//
+// (2) THE GEMM IS TRANSPOSED so the CTA pair shares the depthwise output in hardware.  728 fp32 accumulator columns do
+//     not fit the 512 TMEM columns of one SM, and an N split across CTAs would need the produced A tile copied through
+//     DSMEM (21 B/clk).  Instead the WEIGHTS are the M-side operand and the PIXELS the N-side operand of a
+//     cta_group::2 MMA:   D^T[256 channels, 160 pixels] += W[256, 64] * dw[160, 64]^T.   With cta_group::2 each CTA
+//     supplies HALF of the N-side tile from its own shared memory -- exactly the 80 pixels its own producer warps
+//     computed -- and the tensor core reads both halves for both CTAs.  Three channel tiles (3 x 256 >= 728) keep
+//     3 x 160 = 480 TMEM columns per CTA, so every depthwise k-block is produced once and used for all 728 outputs.
+//
+// Work item = 160 consecutive padded rows (8 padded image rows) per CTA pair; per 64-channel k-block and CTA:
+//   warp 0        TMA: the (80 + 42)-row input window of this CTA's 80 pixels, and three 128 x 64 weight tiles
+//   warps 10-17   depthwise producers: thread = (4 channels, 5 consecutive pixels), the three row triplets slide in
+//                 registers (3 LDS.64 + 18 FFMA2 per output, same tap order as depthwise3x3_pipe_kernel) -> bf16 ->
+//                 this CTA's half of the 128B-swizzled N-side stage
+//   warp 1        (leader CTA) 3 x 4 tcgen05.mma.cta_group::2 (M = 256, N = 160, K = 16) per k-block
+//   warps 2-9     epilogue per channel tile: tcgen05.ld -> BN scale/shift (per-lane constants: lane = channel)
+//                 (+ residual) (ReLU) -> bf16 -> [pixel][channel] staging -> TMA stores of the VALID pixels only
+//                 (one 19-pixel box per image row), so the zero border is never touched.
+// The accumulators are single-buffered (480 of 512 columns); the three channel tiles are released one by one, so the
+// next item's MMAs start on tile 0 while tiles 1 and 2 are still being drained.
+#pragma once
+
+#include "gemm_sm100.cuh"
+
+namespace bq {
+namespace sepmid {
+
+using namespace sm100;
+
+constexpr int kC = 728;                         // channels in and out
+constexpr int kMap = 19;                        // valid map size
+constexpr int kPitch = 20;                      // padded row pitch (19 valid + 1 zero column)
+constexpr int kImgRows = kPitch * kPitch;       // 400 padded rows per image
+constexpr int kItemPx = 160;                    // rows per work item (per CTA pair)
+constexpr int kCtaPx = 80;                      // rows produced per CTA
+constexpr int kWinRows = kCtaPx + 2 * (kPitch + 1);   // 122: halo of 21 rows on either side
+constexpr int kWinBytes = kWinRows * 128;       // 15,616
+constexpr int kNumKb = 12;                      // ceil(728 / 64); the last k-block holds 24 channels (2 k-steps)
+constexpr int kWStages = 6;
+constexpr int kWBytes = 128 * 128;              // 128 weight rows x 64 k
+constexpr int kInStages = 3;
+constexpr int kBStages = 2;
+constexpr int kBBytes = kCtaPx * 128;           // 10,240 (multiple of 1024)
+constexpr int kStepPx = 40;                     // epilogue step: 40 pixels x 128 channels per CTA
+constexpr int kOutTile = kStepPx * 128;         // [40 px][64 ch] bf16
+constexpr int kOutStep = 4 * kOutTile;          // tiles (pixel half, channel box)
+constexpr int kOffW = 0;
+constexpr int kOffB = kOffW + kWStages * kWBytes;
+constexpr int kOffOut = kOffB + kBStages * kBBytes;
+constexpr int kOffIn = kOffOut + 2 * kOutStep;
+constexpr int kOffBar = kOffIn + kInStages * kWinBytes;
+constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignment of the base
+constexpr int kThreads = 576;                   // warp 0 TMA, 1 MMA, 2-9 epilogue, 10-17 producers
+constexpr int kProducerWarps = 8;
+constexpr int kEpiWarps = 8;
+constexpr int kSlackRows = 2 * kItemPx;         // rows allocated past the last image (the last item may overhang)
+
+struct SepMidParams {
+  int n_rows;               // 400 * images in this launch
+  int relu_out;
+  const float* dw;          // [9][728] depthwise taps (bf16-rounded values held in fp32)
+  const float* scale;       // [728] folded BatchNorm
+  const float* shift;
+  const bf16* residual;     // padded layout, nullable
+};
+
+// Cross-CTA hand-off of the depthwise stage (peer CTA's generic-proxy smem writes -> tcgen05.mma issued by the leader):
+// the writer orders its stores ahead of async-proxy reads with fence.proxy.async.shared::cta (MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC.S) and then arrives on the leader's mbarrier.  Cluster-scope release/acquire qualifiers are NOT used:
+// ptxas lowers them to MEMBAR.ALL.GPU on every producer thread and CCTL.IVALL (an L1 flush) on the waiting MMA thread,
+// per k-block -- measured 1.8x slower than the separate kernels.  Shared memory is not cached anywhere, the CTA-level
+// membar completes the stores before the arrive is sent, and the arrive reaches the leader strictly later.
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <bool RELU_IN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box [122 x 64], no swizzle*/,
+                   const __grid_constant__ CUtensorMap tmap_w /*[728, 728] box [128 x 64], SW128*/,
+                   const __grid_constant__ CUtensorMap tmap_out /*[rows, 728] box [19 x 64], no swizzle*/,
+                   const SepMidParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + kOffBar;
+  auto w_full = [&](int s) { return bar0 + 8u * s; };                          // [6]  leader: 2 arrivals + tx
+  auto w_empty = [&](int s) { return bar0 + 8u * (kWStages + s); };            // [6]  both CTAs, multicast commit
+  auto in_full = [&](int s) { return bar0 + 8u * (2 * kWStages + s); };        // [3]  local
+  auto in_empty = [&](int s) { return bar0 + 8u * (2 * kWStages + kInStages + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + s); };       // [2] leader: 16 arrivals
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 2 + s); };  // [2] both CTAs
+  auto acc_full = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 4 + t); }; // [3] both CTAs
+  auto acc_empty = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 7 + t); };// [3] leader: 16 arrivals
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kWStages + 2 * kInStages + 10);
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * (2 * kWStages + 2 * kInStages + 10));
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int n_items = (p.n_rows + kItemPx - 1) / kItemPx;
+  const int my_items = cluster_id < n_items ? (n_items - cluster_id + num_clusters - 1) / num_clusters : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < kWStages; ++s) { mbar_init(w_full(s), 2); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < kInStages; ++s) { mbar_init(in_full(s), 1); mbar_init(in_empty(s), kProducerWarps); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 2 * kProducerWarps); mbar_init(b_empty(s), 1); }
+    for (int t = 0; t < 3; ++t) { mbar_init(acc_full(t), 1); mbar_init(acc_empty(t), 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA: input window of this CTA's 80 pixels + its 128 rows of each weight tile =====================
+    if (lane == 0) {
+      int is = 0; uint32_t iph = 0;
+      int ws = 0; uint32_t wph = 0;
+      for (int li = 0; li < my_items; ++li) {
+        const int p0 = (cluster_id + li * num_clusters) * kItemPx;
+        for (int kb = 0; kb < kNumKb; ++kb) {
+          mbar_wait(in_empty(is), iph ^ 1u);
+          mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
+          tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), kb * 64,
+                      p0 + (int)rank * kCtaPx - (kPitch + 1));
+          if (++is == kInStages) { is = 0; iph ^= 1u; }
+          for (int ct = 0; ct < 3; ++ct) {
+            mbar_wait(w_empty(ws), wph ^ 1u);
+            if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
+            else mbar_arrive_remote(w_full(ws), 0);
+            tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
+            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA; the whole warp walks the loop, one elected lane issues =====================
+    if (is_leader) {
+      if (tmem_base != 0u) __trap();               // all 512 columns are allocated: the base can only be 0 (keeps D addresses immediate)
+      const uint32_t idesc = make_idesc(256, kItemPx);
+      int ws = 0; uint32_t wph = 0;
+      uint32_t q = 0;
+      for (int li = 0; li < my_items; ++li) {
+#pragma unroll 1
+        for (int kb = 0; kb < kNumKb; ++kb, ++q) {
+          const int bs = (int)(q & 1u);
+          mbar_wait(b_full(bs), (q >> 1) & 1u);
+          const uint64_t db = make_smem_desc<128>(smem_base + kOffB + bs * kBBytes);
+#pragma unroll
+          for (int ct = 0; ct < 3; ++ct) {
+            mbar_wait(w_full(ws), wph);
+            if (kb == 0) mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc<128>(smem_base + kOffW + ws * kWBytes);
+            const uint32_t d = (uint32_t)(ct * kItemPx);
+            if (elect_one()) {
+              umma_bf16_2cta(d, da, db, idesc, kb ? 1u : 0u);
+              umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
+              if (kb != kNumKb - 1) {              // the last k-block holds 24 channels: two k-steps
+                umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
+                umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
+              }
+              umma_commit_2cta(w_empty(ws));
+              if (kb == kNumKb - 1) umma_commit_2cta(acc_full(ct));
+              if (ct == 2) umma_commit_2cta(b_empty(bs));
+            }
+            __syncwarp();
+            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue: 128 channels (TMEM lanes) x 160 pixels (columns) per channel tile =====================
+    const int quad = warp & 3;                        // TMEM lane quadrant -> channels quad*32 .. +31 of this CTA's 128
+    const int hh = (warp - 2) >> 2;                   // pixel half: columns hh*80 .. +79
+    const bool leader = (warp == 2 && lane == 0);
+    const int chin = (quad & 1) * 32 + lane;          // channel inside the 64-channel store box
+    const int box = quad >> 1;
+    float sc[3], sh[3];
+    int chn[3];
+#pragma unroll
+    for (int ct = 0; ct < 3; ++ct) {
+      chn[ct] = ct * 256 + (int)rank * 128 + quad * 32 + lane;
+      const bool ok = chn[ct] < kC;
+      sc[ct] = ok ? __ldg(p.scale + chn[ct]) : 0.f;
+      sh[ct] = ok ? __ldg(p.shift + chn[ct]) : 0.f;
+    }
+    const bool has_res = p.residual != nullptr;
+    uint32_t g = 0;                                   // running step counter: staging buffer = g & 1
+    for (int li = 0; li < my_items; ++li) {
+      const int p0 = (cluster_id + li * num_clusters) * kItemPx;
+#pragma unroll
+      for (int ct = 0; ct < 3; ++ct) {
+        mbar_wait(acc_full(ct), (uint32_t)li & 1u);
+        tc_fence_after();
+        for (int s = 0; s < 2; ++s, ++g) {
+          const int px0 = hh * kCtaPx + s * kStepPx;          // first pixel (accumulator column) of this warp's 40
+          uint32_t v[40];
+          {
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + px0);
+            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&v1)[8] = *reinterpret_cast<uint32_t (*)[8]>(&v[32]);
+            tmem_ld_32x32b_x32(t_addr, v0);
+            tmem_ld_32x32b_x8(t_addr + 32u, v1);
+            tmem_ld_wait();
+          }
+          if (s == 1) {                                        // this warp has read its share of channel tile ct
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
+          }
+          float f[40];
+#pragma unroll
+          for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), sc[ct]), sh[ct]);
+          if (has_res && chn[ct] < kC) {
+            const bf16* rp = p.residual + (size_t)(p0 + px0) * kC + chn[ct];
+#pragma unroll
+            for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(f[j], __bfloat162float(rp[(size_t)j * kC]));
+          }
+          if (p.relu_out) {
+#pragma unroll
+            for (int j = 0; j < 40; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (leader) tma_store_wait_read1();                  // the stores of step g - 2 have drained this buffer
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          uint8_t* st = smem_gen + kOffOut + (g & 1u) * kOutStep + (hh * 2 + box) * kOutTile + chin * 2;
+#pragma unroll
+          for (int j = 0; j < 40; ++j) *(bf16*)(st + j * 128) = __float2bfloat16_rn(f[j]);
+          fence_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            // one box of 19 valid pixels per image row; zero rows (y == 19) and rows past the batch are skipped
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+#pragma unroll
+              for (int r2 = 0; r2 < 2; ++r2) {
+                const int row = p0 + (t >> 1) * kCtaPx + s * kStepPx + r2 * kPitch;
+                const int y = (row / kPitch) % kPitch;
+                const int col = ct * 256 + (int)rank * 128 + (t & 1) * 64;
+                if (y != kMap && row < p.n_rows && col < kC)
+                  tma_store_2d(&tmap_out, smem_base + kOffOut + (g & 1u) * kOutStep + t * kOutTile + r2 * kPitch * 128, col, row);
+              }
+            }
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+  } else {
+    // ===================== depthwise producers =====================
+    const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
+    const int c4 = ptid & 15, strip = ptid >> 4;               // 4 channels x 5 consecutive pixels
+    const int b0 = strip * 5;
+    auto ld = [&](const uint8_t* rowp, float2 (&d)[2]) {
+      uint2 raw = *(const uint2*)rowp;
+      if (RELU_IN) {
+        const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+        __nv_bfloat162* hb = (__nv_bfloat162*)&raw;
+        hb[0] = __hmax2(hb[0], z2);
+        hb[1] = __hmax2(hb[1], z2);
+      }
+      d[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
+      d[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+    };
+    const uint32_t total_kb = (uint32_t)my_items * kNumKb;
+    for (uint32_t q = 0; q < total_kb; ++q) {
+      const int kb = (int)(q % kNumKb);
+      const int is = (int)(q % kInStages), bs = (int)(q & 1u);
+      const uint32_t iph = (q / kInStages) & 1u, bph = (q >> 1) & 1u;
+      const int c = kb * 64 + c4 * 4;
+      const bool live = c < kC + 8;                            // the last k-block feeds 2 k-steps (channels 704..735)
+      float2 w[9][2];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < kC) wv = __ldg((const float4*)(p.dw + (size_t)t * kC + c));
+        w[t][0] = make_float2(wv.x, wv.y);
+        w[t][1] = make_float2(wv.z, wv.w);
+      }
+      mbar_wait(in_full(is), iph);
+      mbar_wait(b_empty(bs), bph ^ 1u);
+      if (live) {
+        // window row of output pixel o, tap (dy, dx): o + 21 + dy*20 + dx  ->  top o+{0,1,2}, mid o+{20,21,22}, bottom o+{40,41,42}
+        const uint8_t* win = smem_gen + kOffIn + is * kWinBytes + (size_t)b0 * 128 + c4 * 8;
+        uint8_t* bdst = smem_gen + kOffB + bs * kBBytes;
+        float2 tp[3][2], md[3][2], bt[3][2];
+        ld(win, tp[0]); ld(win + 128, tp[1]);
+        ld(win + 20 * 128, md[0]); ld(win + 21 * 128, md[1]);
+        ld(win + 40 * 128, bt[0]); ld(win + 41 * 128, bt[1]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int i0 = i % 3, i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+          ld(win + (size_t)(i + 2) * 128, tp[i2]);
+          ld(win + (size_t)(i + 22) * 128, md[i2]);
+          ld(win + (size_t)(i + 42) * 128, bt[i2]);
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+          a0 = __ffma2_rn(tp[i0][0], w[0][0], a0); a1 = __ffma2_rn(tp[i0][1], w[0][1], a1);
+          a0 = __ffma2_rn(tp[i1][0], w[1][0], a0); a1 = __ffma2_rn(tp[i1][1], w[1][1], a1);
+          a0 = __ffma2_rn(tp[i2][0], w[2][0], a0); a1 = __ffma2_rn(tp[i2][1], w[2][1], a1);
+          a0 = __ffma2_rn(md[i0][0], w[3][0], a0); a1 = __ffma2_rn(md[i0][1], w[3][1], a1);
+          a0 = __ffma2_rn(md[i1][0], w[4][0], a0); a1 = __ffma2_rn(md[i1][1], w[4][1], a1);
+          a0 = __ffma2_rn(md[i2][0], w[5][0], a0); a1 = __ffma2_rn(md[i2][1], w[5][1], a1);
+          a0 = __ffma2_rn(bt[i0][0], w[6][0], a0); a1 = __ffma2_rn(bt[i0][1], w[6][1], a1);
+          a0 = __ffma2_rn(bt[i1][0], w[7][0], a0); a1 = __ffma2_rn(bt[i1][1], w[7][1], a1);
+          a0 = __ffma2_rn(bt[i2][0], w[8][0], a0); a1 = __ffma2_rn(bt[i2][1], w[8][1], a1);
+          const int pr = b0 + i;
+          uint2 o;
+          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+          ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
+          ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
+          *(uint2*)(bdst + (size_t)pr * 128 + (((c4 >> 1) ^ (pr & 7)) << 4) + (c4 & 1) * 8) = o;
+        }
+      }
+      fence_async_smem();           // generic smem writes -> async proxy (tensor core), and window reads -> next TMA fill
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(b_full(bs)); else mbar_arrive_remote(b_full(bs), 0);
+        mbar_arrive(in_empty(is));
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout converters: [n, 19, 19, 728] <-> padded [n * 400, 728] (valid pixels only; the zero border is never written)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pad_copy_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n_img, int to_padded) {
+  constexpr int cv = kC / 8;                                   // 91 x 16 B per pixel
+  const int64_t total = (int64_t)n_img * kMap * kMap * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv);
+    int64_t pix = idx / cv;
+    const int x = (int)(pix % kMap);
+    pix /= kMap;
+    const int y = (int)(pix % kMap);
+    const int img = (int)(pix / kMap);
+    const int64_t dense = (((int64_t)img * kMap + y) * kMap + x) * kC + c8 * 8;
+    const int64_t padded = ((int64_t)img * kImgRows + y * kPitch + x) * kC + c8 * 8;
+    if (to_padded) *(uint4*)(out + padded) = __ldg((const uint4*)(in + dense));
+    else *(uint4*)(out + dense) = __ldg((const uint4*)(in + padded));
+  }
+}
+
+}  // namespace sepmid
+}  // namespace bq

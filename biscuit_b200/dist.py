@@ -76,6 +76,87 @@ def all_gather_groups(msg: np.ndarray, group=None, device=None):
     return np.concatenate(parts, axis=0) if parts else msg
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# byte-level collectives (tensor all-gathers only: no pickled objects, so the exchange stays on NCCL / NVLink)
+# ----------------------------------------------------------------------------------------------------------------
+def _dist_state(group=None):
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return None, 1, 0
+    return dist, dist.get_world_size(group), dist.get_rank(group)
+
+
+def _collective_device(dist, group, device):
+    import torch
+    return torch.device("cpu") if dist.get_backend(group) == "gloo" else torch.device(device if device is not None else "cuda")
+
+
+def all_gather_meta(values, group=None, device=None):
+    """int64 [k] per rank -> int64 [world, k] (one small all-gather: row counts, group counts, error codes ...)."""
+    import torch
+    dist, world, _ = _dist_state(group)
+    v = np.asarray(values, dtype=np.int64).reshape(1, -1)
+    if world == 1:
+        return v
+    dev = _collective_device(dist, group, device)
+    t = torch.from_numpy(v[0].copy()).to(dev)
+    out = torch.empty((world, v.shape[1]), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy()
+
+
+def all_gather_bytes(buf, sizes, group=None, device=None):
+    """Variable-length all-gather of raw bytes when every rank already knows all `sizes` (from `all_gather_meta`).
+    -> list of uint8 arrays, one per rank, in rank order."""
+    import torch
+    dist, world, _ = _dist_state(group)
+    buf = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    if world == 1:
+        return [buf]
+    sizes = [int(x) for x in sizes]
+    pad = max(max(sizes), 1)
+    dev = _collective_device(dist, group, device)
+    t = torch.zeros(pad, dtype=torch.uint8, device=dev)
+    if buf.shape[0]:
+        t[: buf.shape[0]] = torch.from_numpy(buf).to(dev)
+    out = torch.empty((world, pad), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    host = out.cpu().numpy()
+    return [host[r, : sizes[r]] for r in range(world)]
+
+
+def pack_names(names):
+    """slide / patient names -> (uint8 buffer of the utf-8 bytes, int32 lengths): strings cross ranks as tensors"""
+    enc = [str(x).encode("utf-8") for x in names]
+    lens = np.asarray([len(e) for e in enc], dtype=np.int32)
+    return np.frombuffer(b"".join(enc), dtype=np.uint8).copy(), lens
+
+
+def unpack_names(buf, lens):
+    out, o = [], 0
+    raw = np.asarray(buf, dtype=np.uint8).tobytes()
+    for n in np.asarray(lens, dtype=np.int64):
+        out.append(raw[o:o + n].decode("utf-8"))
+        o += int(n)
+    return out
+
+
+def pack_tiles(y_pred, uncertainty, y_true):
+    """per-tile (pred, unc, label) triples -> bytes (2 * itemsize + 1 B per tile: 9 B for float32 tables)"""
+    yp, un = np.ascontiguousarray(y_pred), np.ascontiguousarray(uncertainty)
+    yt = np.ascontiguousarray(y_true, dtype=np.uint8)
+    return np.concatenate([yp.view(np.uint8).reshape(-1), un.view(np.uint8).reshape(-1), yt])
+
+
+def unpack_tiles(buf, n, dtype):
+    isz = np.dtype(dtype).itemsize
+    b = np.asarray(buf, dtype=np.uint8)
+    yp = b[: n * isz].copy().view(dtype)
+    un = b[n * isz: 2 * n * isz].copy().view(dtype)
+    yt = b[2 * n * isz: 2 * n * isz + n].copy()
+    return yp, un, yt
+
+
 def unpack_groups(msg: np.ndarray, dtype):
     """-> dict of arrays for the surviving groups, ordered by first surviving row (first appearance)."""
     alive = msg[:, 1] > 0

@@ -282,19 +282,23 @@ def _group_stage(tab: _DeviceTable, df, level, tile_uq_eff, pred_thresh, factori
     alive = np.flatnonzero(cnt > 0)
     order = alive[np.argsort(first[alive], kind="stable")]           # first appearance after filter
     levels = [uniques[i] for i in order]                              # :190
-    yp, u = gp[order], gu[order]
-    yt = gt[order].astype(np.uint8)                                   # :197-200 truncation
+    return _group_table(tab.ctx, level, levels, gp[order], gu[order], gt[order].astype(np.uint8), pred_thresh)
+
+
+def _group_table(ctx, level, levels, yp, u, yt, pred_thresh):
+    """threshold.py:197-245 on the per-group means (already in first-appearance order, `yt` truncated to uint8,
+    :197-200): optional Youden detection on the group ROC, then the group DataFrame."""
     if not len(yt):                                                   # :205-206
         raise errors.ROCFailedError("Unable to generate ROC; preds are empty.")
     if _is_detect(pred_thresh):                                       # :217-223
-        r = _roc(tab.ctx, yp, yt)
+        r = _roc(ctx, yp, yt)
         if r.status != 0:
             raise errors.ROCFailedError(f"Unable to generate {level}-level ROC")
         pred_thresh = np.float64(r.threshold)
         log.debug(f"Using detected prediction threshold: {pred_thresh:.4f}")
     else:
         log.debug(f"Using {level} prediction threshold: {pred_thresh:.4f}")   # :225
-    cols = _group_columns(tab.ctx, yp, u, yt, pred_thresh, pred_thresh, _ffi.KEEP_ALL, 0.0)
+    cols = _group_columns(ctx, yp, u, yt, pred_thresh, pred_thresh, _ffi.KEEP_ALL, 0.0)
     l_df = pd.DataFrame({                                             # :235-244
         level: pd.Series(levels),
         "error": pd.Series(cols["error"]),
@@ -388,6 +392,11 @@ def apply(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
             log.error("Unable to process slide predictions")
             return {k: None for k in _RESULT_KEYS}, None              # :310-317
         ctx = tab.ctx
+    return _apply_group_level(ctx, s_df, slide_uq, slide_pred, keep, level, n_before)
+
+
+def _apply_group_level(ctx, s_df, slide_uq, slide_pred, keep, level, n_before):
+    """threshold.py:323-361: group-level UQ filter, AUROC, percent included and the confusion counts."""
     yp, u, yt = s_df["y_pred"].to_numpy(), s_df["uncertainty"].to_numpy(), s_df["y_true"].to_numpy()
     if slide_uq:                                                      # :323-330
         log.debug(f"Using {level} uncertainty threshold of {slide_uq:.5f}")
@@ -410,78 +419,208 @@ def apply(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
     return results, s_df
 
 
+# ----------------------------------------------------------------------------------------
+# cohort sharded over GPUs: one process per GPU, slide-aligned shards
+# ----------------------------------------------------------------------------------------
+_ERR_NONE, _ERR_NAN, _ERR_NONFINITE, _ERR_LABEL, _ERR_EMPTY = 0, 1, 2, 3, 4
+
+
+def _raise_shard_error(code):
+    """the same exception on every rank (a rank that raised alone would leave the others blocked in a collective)"""
+    if code == _ERR_NAN:
+        raise errors.PredsContainNaNError
+    if code == _ERR_NONFINITE:
+        raise ValueError("Input contains infinity or a value too large for dtype.")
+    if code == _ERR_LABEL:
+        raise ValueError("multiclass format is not supported")
+    if code == _ERR_EMPTY:
+        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
+
+
+def _shard_local(df, level, patients, tile_pred, tile_uq_eff_fn):
+    """Local half of a sharded call: validation, tile processing (mutates the shard like the reference mutates the
+    table) and the reference-order per-slide reduction of THIS rank's slides.  Never raises: the error code travels
+    with the size exchange so that every rank fails together.  An empty shard (more ranks than slides) contributes
+    zero groups."""
+    out = {"err": _ERR_NONE, "n_rows": len(df), "names": [], "n_keys": 0, "msg": np.zeros((0, 6), np.float64),
+           "dtype": np.dtype(df["y_pred"].to_numpy().dtype) if "y_pred" in df.columns and len(df) else None,
+           "ctx": _ffi.default_context()}
+    if len(df) == 0:
+        return out
+    with _open_table(df) as tab:
+        out["ctx"], out["dtype"] = tab.ctx, tab.dtype
+        try:
+            _tile_stage(tab, df, tile_pred, patients)
+        except errors.PredsContainNaNError:
+            out["err"] = _ERR_NAN
+            return out
+        except ValueError as e:
+            out["err"] = _ERR_LABEL if "multiclass" in str(e) else _ERR_NONFINITE
+            return out
+        codes, uniques = _factorize(df[level])
+        out["n_keys"] = len(uniques) + int((codes < 0).any())
+        out["names"] = [str(u) for u in uniques]
+        tab.set_groups(codes, len(uniques))
+        tab.set_filter(tile_uq_eff_fn(tab.dtype))
+        gp, gu, gt, cnt, first = tab.group_reduce()
+    out["local"] = (gp, gu, gt, cnt, first)
+    return out
+
+
+def _exchange_groups(loc, group):
+    """meta all-gather (sizes + error codes) and ONE payload all-gather (per-slide aggregates + slide names as utf-8
+    tensors): -> (groups dict in global first-appearance order, all names, keys before the tile filter, dtype)."""
+    from . import dist as bdist
+    name_buf, name_len = bdist.pack_names(loc["names"])
+    L = len(loc["names"])
+    dcode = -1 if loc["dtype"] is None else (0 if loc["dtype"] == np.float32 else 1)
+    device = f"cuda:{loc['ctx'].device}"
+    meta = bdist.all_gather_meta([loc["n_rows"], L, loc["n_keys"], loc["err"], name_buf.shape[0], dcode],
+                                 group=group, device=device)
+    errs = meta[:, 3]
+    if errs.any():
+        _raise_shard_error(int(errs[errs != 0][0]))
+    if int(meta[:, 0].sum()) == 0:
+        _raise_shard_error(_ERR_EMPTY)
+    _, _, rank = bdist._dist_state(group)
+    code_off, row_off = int(meta[:rank, 1].sum()), int(meta[:rank, 0].sum())
+    if L:
+        gp, gu, gt, cnt, first = loc["local"]
+        msg = bdist.pack_groups(code_off, cnt, first, row_off, gp, gu, gt)
+    else:
+        msg = np.zeros((0, 6), np.float64)
+    payload = np.concatenate([msg.view(np.uint8).reshape(-1), name_len.view(np.uint8).reshape(-1), name_buf])
+    sizes = [int(m[1]) * 52 + int(m[4]) for m in meta]              # 48 B of aggregates + 4 B name length per slide
+    parts = bdist.all_gather_bytes(payload, sizes, group=group, device=device)
+    msgs, names = [], []
+    for m, part in zip(meta, parts):
+        Lr, nb = int(m[1]), int(m[4])
+        msgs.append(part[: Lr * 48].copy().view(np.float64).reshape(Lr, 6))
+        lens = part[Lr * 48: Lr * 52].copy().view(np.int32)
+        names += bdist.unpack_names(part[Lr * 52: Lr * 52 + nb], lens)
+    dcodes = meta[:, 5][meta[:, 5] >= 0]
+    dtype = np.dtype(np.float64 if (dcodes == 1).any() else np.float32)
+    g = bdist.unpack_groups(np.concatenate(msgs, axis=0), dtype)
+    return g, names, int(meta[:, 2].sum()), dtype
+
+
 def apply_sharded(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, keep="high_confidence",
                   patients=None, level="slide", group=None):
     """`apply` for a cohort sharded over ranks (one process per GPU, torch.distributed initialised).
 
     Every rank passes ITS contiguous, slide-aligned shard of the tile table (see `dist.shard_bounds`;
-    a slide / patient must not straddle ranks).  Tile processing and the reference-order slide
-    reduction run locally on each GPU; the per-slide aggregates (<= 48 B per slide) are all-gathered
-    once and the group-level thresholding runs replicated, so every rank returns the same
-    (results, s_df) `apply` would return on the concatenated table."""
-    import torch.distributed as tdist
-    from . import dist as bdist
+    a slide / patient must not straddle ranks; a shard may be empty).  Tile processing and the
+    reference-order slide reduction run locally on each GPU; the per-slide aggregates (48 B per slide)
+    and the slide names (utf-8 tensors, no pickling) are all-gathered ONCE after a small size / error-code
+    exchange, and the group-level thresholding runs replicated, so every rank returns the same
+    (results, s_df) `apply` would return on the concatenated table -- and every rank raises the same
+    exception when any shard fails validation.  Thresholds must be numeric: 'detect' is resolved on the
+    whole cohort by `detect_sharded`."""
     assert keep in ("high_confidence", "low_confidence")
     assert not (level == "patient" and patients is None)
+    if _is_detect(tile_pred) or _is_detect(slide_pred):
+        raise ValueError("apply_sharded needs numeric prediction thresholds (a per-shard 'detect' would differ "
+                         "between ranks): use detect_sharded / from_cv_sharded first")
     log.debug(f"Applying tile UQ threshold of {tile_uq:.5f}")
     if patients:
         df["patient"] = df["slide"].map(patients)
     df[level]
     _check_columns(df)
-    world = tdist.get_world_size(group) if tdist.is_available() and tdist.is_initialized() else 1
-    with _open_table(df) as tab:
-        _tile_stage(tab, df, tile_pred, patients)
-        codes, uniques = _factorize(df[level])
-        n_keys = len(uniques) + int((codes < 0).any())
-        tile_uq_eff = _cmp_scalar(tile_uq, tab.dtype) if tile_uq else None
-        tab.set_groups(codes, len(uniques))
-        tab.set_filter(tile_uq_eff)
-        gp, gu, gt, cnt, first = tab.group_reduce()
-        ctx, dtype = tab.ctx, tab.dtype
-    names = [str(u) for u in uniques]
-    if world > 1:
-        meta = [None] * world
-        tdist.all_gather_object(meta, (len(uniques), len(df), n_keys, names), group=group)
-        rank = tdist.get_rank(group)
-        code_off = sum(m[0] for m in meta[:rank])
-        row_off = sum(m[1] for m in meta[:rank])
-        n_before = sum(m[2] for m in meta)
-        all_names = [nm for m in meta for nm in m[3]]
-    else:
-        code_off, row_off, n_before, all_names = 0, 0, n_keys, names
-    msg = bdist.pack_groups(code_off, cnt, first, row_off, gp, gu, gt)
-    g = bdist.unpack_groups(bdist.all_gather_groups(msg, group=group, device=f"cuda:{ctx.device}"), dtype)
-    yp, u, yt = g["y_pred"], g["uncertainty"], g["y_true"]
-    if not len(yt):
+    loc = _shard_local(df, level, patients, tile_pred, lambda dt: _cmp_scalar(tile_uq, dt) if tile_uq else None)
+    g, names, n_before, _ = _exchange_groups(loc, group)
+    levels = [names[c] for c in g["code"]]
+    try:
+        s_df, _ = _group_table(loc["ctx"], level, levels, g["y_pred"], g["uncertainty"], g["y_true"], slide_pred)
+    except errors.ROCFailedError:
         log.error("Unable to process slide predictions")
         return {k: None for k in _RESULT_KEYS}, None
-    base = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, _ffi.KEEP_ALL, 0.0)
-    s_df = pd.DataFrame({
-        level: pd.Series([all_names[c] for c in g["code"]]),
-        "error": pd.Series(base["error"]),
-        "uncertainty": pd.Series(u),
-        "correct": base["correct"].view(np.bool_),
-        "incorrect": pd.Series(base["incorrect"]).astype(int),
-        "y_true": pd.Series(yt),
-        "y_pred": pd.Series(yp),
-        "y_pred_bin": pd.Series(base["y_pred_bin"].view(np.bool_)).astype(int),
-    })
-    if slide_uq:
-        mode = _ffi.KEEP_HIGH if keep == "high_confidence" else _ffi.KEEP_LOW
-        uq_eff = _cmp_scalar(slide_uq, u.dtype)
+    return _apply_group_level(loc["ctx"], s_df, slide_uq, slide_pred, keep, level, n_before)
+
+
+def detect_sharded(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pred="detect",
+                   patients=None, group=None):
+    """`detect` for a table sharded over ranks (reference threshold.py:364-475 on the concatenated table).
+
+    The tile-level ROCs (`y_true ~ y_pred`, `incorrect ~ uncertainty`) run over ALL tiles of the cohort, so the
+    per-tile `(pred, unc, label)` triples (9 B per tile for float32 tables) are all-gathered -- the one real
+    exchange step of the path -- and the ROC kernels run on the gathered table on every GPU
+    (deterministic integer/fp64 kernels: replicated, identical thresholds, no broadcast needed).  The slide
+    reduction stays local and bit-exact (slide-aligned shards), its aggregates are all-gathered as in
+    `apply_sharded`, and the slide-level detection runs replicated.  Returns what `detect` returns, on every rank."""
+    from . import dist as bdist
+    none4 = {k: None for k in _THRESH_KEYS}
+    _check_columns(df)
+    ctx = _ffi.default_context()
+    device = f"cuda:{ctx.device}"
+    n_local = len(df)
+    yp_l = _float_col(df["y_pred"].to_numpy()) if n_local else np.zeros(0, np.float32)
+    un_l = _float_col(df["uncertainty"].to_numpy()) if n_local else np.zeros(0, np.float32)
+    if yp_l.dtype != un_l.dtype:
+        yp_l, un_l = yp_l.astype(np.float64), un_l.astype(np.float64)
+    need_tiles = _is_detect(tile_pred) or _is_detect(tile_uq)
+    if need_tiles:
+        # ---- exchange 1: sizes + column dtype, then the tile triples
+        meta = bdist.all_gather_meta([n_local, -1 if not n_local else int(yp_l.dtype == np.float64)], group=group, device=device)
+        wide = bool((meta[:, 1] == 1).any())
+        dt = np.dtype(np.float64 if wide else np.float32)
+        buf = bdist.pack_tiles(yp_l.astype(dt, copy=False), un_l.astype(dt, copy=False),
+                               _label_col(df["y_true"].to_numpy()) if n_local else np.zeros(0, np.uint8))
+        parts = bdist.all_gather_bytes(buf, [int(m[0]) * (2 * dt.itemsize + 1) for m in meta], group=group, device=device)
+        cols = [bdist.unpack_tiles(part, int(m[0]), dt) for m, part in zip(meta, parts)]
+        yp_g, un_g, yt_g = (np.concatenate([c[i] for c in cols]) for i in range(3))
+        with _DeviceTable(yp_g, un_g, yt_g, ctx=ctx) as tab:
+            n_nan, n_nonfinite, n_unc_nonfinite, n_badlabel = tab.validate()
+            if n_nan:
+                log.error("Tile-level predictions contain NaNs; unable to process.")
+                return none4, None
+            if n_nonfinite:
+                raise ValueError("Input contains infinity or a value too large for dtype.")
+            if n_badlabel:
+                raise ValueError("multiclass format is not supported")
+            if _is_detect(tile_pred):
+                r = tab.tile_roc(_ffi.SCORE_Y_PRED, _ffi.LABEL_Y_TRUE)
+                if r.status == 0:
+                    tile_pred = np.float64(r.threshold)
+                elif r.status == 1:
+                    tile_pred = 0.5
+                else:
+                    raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required.")
+            tab.tile_process(_cmp_scalar(tile_pred, tab.dtype))
+            if _is_detect(tile_uq):
+                if n_unc_nonfinite:
+                    raise ValueError("Input contains NaN or infinity.")
+                tile_uq = _youden_or_raise(tab.tile_roc(_ffi.SCORE_UNCERTAINTY, _ffi.LABEL_INCORRECT))
+    if isinstance(tile_uq, _FLOAT_TYPES):
+        def tile_uq_eff_fn(dtype, t=tile_uq):
+            return _cmp_scalar(t, dtype) if not isinstance(t, np.float64) or True else float(t)
     else:
-        mode, uq_eff = _ffi.KEEP_ALL, 0.0
-    cols = _group_columns(ctx, yp, u, yt, slide_pred, slide_pred, mode, uq_eff)
-    if slide_uq:
-        s_df = s_df.loc[cols["include"].view(np.bool_)]
-    auc = _auc_included(ctx, yp, yt, cols["include"])
-    tp, fp, tn, fn = cols["confusion"]
-    with np.errstate(invalid="ignore", divide="ignore"):
-        results = {"auc": auc, "percent_incl": len(s_df) / n_before,
-                   "acc": (tp + tn) / (tp + tn + fp + fn),
-                   "sensitivity": tp / (tp + fn),
-                   "specificity": tn / (tn + fp)}
-    return results, s_df
+        if not _is_detect(tile_uq):
+            log.debug("Not performing tile-level uncertainty thresholding.")
+        tile_uq = None
+
+        def tile_uq_eff_fn(dtype):
+            return None
+    # ---- local tile processing + slide reduction, exchange 2: per-slide aggregates
+    loc = _shard_local(df, "slide", patients, tile_pred, tile_uq_eff_fn)
+    try:
+        g, names, _, _ = _exchange_groups(loc, group)
+    except errors.PredsContainNaNError:
+        log.error("Tile-level predictions contain NaNs; unable to process.")
+        return none4, None
+    levels = [names[c] for c in g["code"]]
+    try:
+        s_df, slide_pred = _group_table(loc["ctx"], "slide", levels, g["y_pred"], g["uncertainty"], g["y_true"], slide_pred)
+    except errors.ROCFailedError:
+        log.error("Unable to process slide predictions")
+        return none4, None
+    slide_uq, auc = _detect_group_level(loc["ctx"], s_df, slide_uq, slide_pred)
+    return {"tile_uq": tile_uq, "slide_uq": slide_uq, "tile_pred": tile_pred, "slide_pred": slide_pred}, auc
+
+
+def from_cv_sharded(dfs, group=None, **kwargs):
+    """`from_cv` with every fold table sharded over the ranks: `detect_sharded` per fold, same fold-skipping and
+    min / max / mean reduction over folds as the reference (threshold.py:478-557)."""
+    return _from_cv(dfs, lambda df, **kw: detect_sharded(df, group=group, **kw), kwargs, require_patient=False)
 
 
 def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pred="detect",
@@ -521,6 +660,13 @@ def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pr
             log.error("Unable to process slide predictions")
             return none4, None                                        # :439-441
         ctx = tab.ctx
+    slide_uq, auc = _detect_group_level(ctx, s_df, slide_uq, slide_pred)
+    return {"tile_uq": tile_uq, "slide_uq": slide_uq,
+            "tile_pred": tile_pred, "slide_pred": slide_pred}, auc
+
+
+def _detect_group_level(ctx, s_df, slide_uq, slide_pred):
+    """threshold.py:444-468: slide-level UQ threshold (Youden on incorrect ~ uncertainty) and the AUROC of the kept slides."""
     yp, u, yt = s_df["y_pred"].to_numpy(), s_df["uncertainty"].to_numpy(), s_df["y_true"].to_numpy()
     include = None
     if _is_detect(slide_uq):                                          # :444-460
@@ -536,9 +682,7 @@ def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pr
     else:
         log.debug("Not performing slide-level uncertainty thresholding.")
         slide_uq = 0.5                                                # :461-463
-    auc = _auc_included(ctx, yp, yt, include)                         # :468
-    return {"tile_uq": tile_uq, "slide_uq": slide_uq,
-            "tile_pred": tile_pred, "slide_pred": slide_pred}, auc
+    return slide_uq, _auc_included(ctx, yp, yt, include)              # :468
 
 
 def from_cv(dfs, **kwargs):
@@ -552,7 +696,12 @@ def from_cv(dfs, **kwargs):
         **kwargs: forwarded to :func:`detect` (tile_uq, slide_uq, tile_pred, slide_pred, patients).
 
     Raises ValueError for missing columns and ThresholdError when no fold yields a threshold."""
-    required = ("y_true", "y_pred", "uncertainty", "slide", "patient")
+    return _from_cv(dfs, detect, kwargs)
+
+
+def _from_cv(dfs, detect_fn, kwargs, require_patient=True):
+    required = ("y_true", "y_pred", "uncertainty", "slide", "patient") if require_patient else \
+               ("y_true", "y_pred", "uncertainty", "slide")
     skip_tile = "tile_uq_thresh" in kwargs and kwargs["tile_uq_thresh"] is None     # :513-516
     skip_slide = "slide_uq_thresh" in kwargs and kwargs["slide_uq_thresh"] is None
     k_tile, k_slide, k_tile_pred, k_slide_pred = [], [], [], []
@@ -561,7 +710,7 @@ def from_cv(dfs, **kwargs):
         if not all(col in df.columns for col in required):            # :520-524
             raise ValueError(f"DataFrame missing columns, expected {required}, got: "
                              f"{', '.join(df.columns.tolist())}")
-        thresholds, _ = detect(df, **kwargs)                          # :525
+        thresholds, _ = detect_fn(df, **kwargs)                       # :525
         if thresholds["tile_uq"] is None or thresholds["slide_uq"] is None:   # :526-528
             log.debug(f"Skipping CV #{idx}, unable to detect threshold")
             continue

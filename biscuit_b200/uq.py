@@ -164,7 +164,7 @@ class UncertaintyInterface:
         return out[: int(np.prod(s))].reshape(s).copy()
 
     KERNEL_FAMILIES = ("tile_stats", "conv1", "gemm_conv2", "gemm_pointwise", "depthwise", "maxpool_add",
-                       "subsample", "gap", "head_gemm", "mc_expand", "head_final", "head_fused", "sepconv_fused")
+                       "subsample", "gap", "head_gemm", "mc_expand", "head_final", "head_fused", "sepconv_fused", "sepconv_mid")
 
     def set_profiling(self, level: int):
         """0 off, 1 per-stage CUDA-event times, 2 per-kernel-family times + algorithmic work"""

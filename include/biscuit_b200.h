@@ -179,7 +179,7 @@ int bq_model_last_stage_ms(bq_model* m, float ms[8]);
 enum {
   BQ_K_STATS = 0, BQ_K_CONV1 = 1, BQ_K_GEMM_CONV2 = 2, BQ_K_GEMM_PW = 3, BQ_K_DW = 4, BQ_K_POOLADD = 5,
   BQ_K_SUBSAMPLE = 6, BQ_K_GAP = 7, BQ_K_HEAD_GEMM = 8, BQ_K_MC_EXPAND = 9, BQ_K_HEAD_FINAL = 10,
-  BQ_K_HEAD_FUSED = 11, BQ_K_SEP_FUSED = 12,
+  BQ_K_HEAD_FUSED = 11, BQ_K_SEP_FUSED = 12, BQ_K_SEP_MID = 13,
   BQ_PROFILE_KINDS = 16
 };
 int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flops[BQ_PROFILE_KINDS],

@@ -373,3 +373,37 @@ def test_config1_end_to_end_512_tiles_4_slides(weights, bench_iface):
         far = np.abs(s2["uncertainty"].to_numpy().astype(np.float64) - slide_uq) > 4e-3
         common = [s for s in s2["slide"][far] if s in set(s1["slide"])]
         assert len(common) == int(far.sum()), (list(s1["slide"]), list(s2["slide"]))
+
+
+def test_fused_middle_flow_agrees_with_separate_kernels():
+    """Default: the 728-wide middle flow runs in `sepconv_mid_kernel` (depthwise produced on-chip into the N-side
+    operand of a transposed cta_group::2 GEMM, zero-padded flattened layout).  BQ_SEPMID=off: stand-alone depthwise
+    kernel + pointwise GEMM.  Same bf16 rounding points and the same fp32 depthwise tap order; only the tensor-core
+    accumulation order may differ -> bf16-level agreement on the features (and usually bit-identity)."""
+    code = (
+        "import numpy as np, sys, torch\n"
+        "from oracle import synth\n"
+        "from biscuit_b200.weights import random_init\n"
+        "from biscuit_b200.uq import UncertaintyInterface\n"
+        "i = UncertaintyInterface(random_init(seed=1), max_batch=48)\n"
+        "t = torch.from_numpy(synth.tiles_u8(25, seed=4)).cuda().repeat(5, 1, 1, 1).contiguous()\n"
+        "m, s, f = i.predict(t, T=5, seed=5, return_features=True)\n"
+        "b12 = i.debug_stage(synth.tiles_u8(3, seed=4), 'block12')\n"
+        "np.save(sys.argv[1], np.concatenate([m.ravel(), s.ravel(), f.ravel(), b12.ravel()]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("off", "on"):
+        path = f"/tmp/bq_sepmid_{mode}.npy"
+        env = dict(os.environ, BQ_SEPMID=mode, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
+        outs.append(np.load(path))
+    a, b = outs
+    n = 125
+    d = np.abs(a - b)
+    print("sepmid on vs off: bit-identical" if a.tobytes() == b.tobytes() else
+          f"sepmid on vs off: max d mean/std {d[:4 * n].max():.3e}, features {d[4 * n:4 * n + n * 2048].max():.3e}, block12 {d[4 * n + n * 2048:].max():.3e}")
+    assert d[:4 * n].max() <= 3e-3
+    f = a[4 * n:4 * n + n * 2048]
+    assert d[4 * n:4 * n + n * 2048].max() <= 2e-2 * np.abs(f).max()
+    b12 = a[4 * n + n * 2048:]
+    assert d[4 * n + n * 2048:].max() <= 3e-2 * np.abs(b12).max()
