@@ -640,7 +640,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_before();
   cluster_sync_all();                        // barriers initialised + TMEM allocated in both CTAs
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // warp-uniform for the compiler (MMA operands live in uniform registers)
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA: its A rows + its half of B) =====================
@@ -670,7 +670,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA; the whole warp walks the loop, one elected lane issues =====================
     if (is_leader) {
-      if (tmem_base != 0u) __trap();             // all 512 columns are allocated: the base can only be 0
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -681,7 +680,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t idesc = make_idesc(2 * kBM, WIDE ? 256 : n_cols);
         const uint32_t idesc2 = make_idesc(2 * kBM, WIDE ? n_cols - 256 : 16);
         mbar_wait(tempty_bar(as), aph ^ 1u);
-        const uint32_t d_tmem = (uint32_t)(as * kBNMax);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
@@ -858,7 +857,7 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
   const uint32_t tmem_slot = b_bar + 8u;
   volatile uint32_t* tmem_slot_ptr =
       (volatile uint32_t*)(smem_gen + kC2BBytes + kC2Stages * kC2WinBytes + 8 * (2 * kC2Stages + 2 * kC2AccStages + 1));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = (p.M + kBM - 1) / kBM;
 
   if (warp == 0 && lane == 0) {
@@ -873,7 +872,7 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -889,9 +888,9 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
       }
     }
   } else if (warp == 1 || warp == 6) {
-    // two issuing warps take alternate tiles: one thread sustains only ~1 tcgen05.mma per 80 cycles, and these
-    // 128x64x16 MMAs need 32 cycles of tensor pipe each
-    if (lane == 0) {
+    // two issuing warps take alternate tiles; each walks its loop as a converged warp and one elected lane issues (an
+    // `if (lane == 0)` region costs ~25 instructions per tcgen05.mma, see elect_one())
+    {
       mbar_wait(b_bar, 0);
       const uint32_t idesc = make_idesc(kBM, 64);
       const uint64_t b_base = make_smem_desc<64>(b_smem);
@@ -909,16 +908,19 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
         tc_fence_after();
         const uint64_t a_base = make_smem_desc<64>(win0 + s * kC2WinBytes);
         const uint32_t d = tmem_base + (uint32_t)(as * 64);
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int roff = ((t / 3) * p.in_w + (t % 3)) * 64;           // tap = rows shifted inside the window
+          for (int t = 0; t < 9; ++t) {
+            const int roff = ((t / 3) * p.in_w + (t % 3)) * 64;           // tap = rows shifted inside the window
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16(d, a_base + (uint64_t)((roff + k * 32) >> 4), b_base + (uint64_t)((t * 4096 + k * 32) >> 4), idesc,
-                      (t | k) ? 1u : 0u);
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d, a_base + (uint64_t)((roff + k * 32) >> 4), b_base + (uint64_t)((t * 4096 + k * 32) >> 4), idesc,
+                        (t | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(as));
         }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(as));
+        __syncwarp();
       }
     }
   } else if ((warp >= 2 && warp <= 5) || warp >= 7) {

@@ -577,6 +577,8 @@ int build_plan(bq_model* m) {
       if ((r = make_tmap(ctx, &op.ta, P(src), rows, kC, kC, kWinRows, 64, true))) return r;
       if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, kC, kC, kC, 128, 64))) return r;
       if ((r = make_tmap(ctx, &op.tc, P(dst), rows, kC, kC, kMap, 64, true))) return r;
+      op.tr = op.tc;
+      if (res >= 0 && (r = make_tmap(ctx, &op.tr, P(res), rows, kC, kC, kStepPx, 64, true))) return r;
       m->plan.push_back(op);
       return BQ_OK;
     };
@@ -736,9 +738,9 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       const double px_n = (double)nb * op.H * op.W;
       KScope ks(m, BQ_K_SEP_MID, 2.0 * px_n * op.C * (op.C + 9.0), act * px_n * op.C * (sm.residual ? 3.0 : 2.0));
       if (op.relu_in)
-        bq::sepmid::sepconv_mid_kernel<true><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, sm);
+        bq::sepmid::sepconv_mid_kernel<true><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sm);
       else
-        bq::sepmid::sepconv_mid_kernel<false><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, sm);
+        bq::sepmid::sepconv_mid_kernel<false><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sm);
       break;
     }
     case OP_PADCOPY: {

@@ -79,7 +79,7 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
   float* s_scale = (float*)(smem_gen + kOffScale);
   float* s_shift = s_scale + 256;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int px_tiles = (p.W + kPW - 1) / kPW, py_tiles = (p.H + kPH - 1) / kPH;
   const int per_img = px_tiles * py_tiles;
   const int n_items = p.n_img * per_img;
@@ -106,7 +106,7 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // warp-uniform for the compiler
 
   if (warp == 0) {
     // ===================== TMA: halo patch + weight k-block =====================
@@ -140,16 +140,16 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: converged warp, one elected lane issues (see elect_one()) =====================
+    {
       const uint32_t idesc = make_idesc(128, p.N);
       int as = 0; uint32_t aph = 0;                // A / B rings advance together (one step per k-block)
       int cs = 0; uint32_t cph = 0;                // accumulator stage per item
       int gk = 0;                                  // k-blocks issued so far (resident weights: only the first two wait for B)
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         mbar_wait(acc_empty(cs), cph ^ 1u);
-        tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(cs * 256);
+#pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(a_full(as), aph);
           if (!b_resident || gk < kBStages) mbar_wait(b_full(as), aph);
@@ -157,11 +157,16 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
           tc_fence_after();
           const uint64_t da = make_smem_desc<128>(smem_base + kOffA + as * kABytes);
           const uint64_t db = make_smem_desc<128>(smem_base + kOffB + as * kBBytes);
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(a_empty(as));
-          if (!b_resident) umma_commit(b_empty(as));
-          if (kb == num_kb - 1) umma_commit(acc_full(cs));
+          if (elect_one()) {
+            umma_bf16(d, da, db, idesc, kb ? 1u : 0u);
+            umma_bf16(d, da + 2u, db + 2u, idesc, 1u);
+            umma_bf16(d, da + 4u, db + 4u, idesc, 1u);
+            umma_bf16(d, da + 6u, db + 6u, idesc, 1u);
+            umma_commit(a_empty(as));
+            if (!b_resident) umma_commit(b_empty(as));
+            if (kb == num_kb - 1) umma_commit(acc_full(cs));
+          }
+          __syncwarp();
           if (++as == 2) { as = 0; aph ^= 1u; }
         }
         if (++cs == 2) { cs = 0; cph ^= 1u; }

@@ -60,7 +60,8 @@ constexpr int kOutStep = 4 * kOutTile;          // tiles (pixel half, channel bo
 constexpr int kOffW = 0;
 constexpr int kOffB = kOffW + kWStages * kWBytes;
 constexpr int kOffOut = kOffB + kBStages * kBBytes;
-constexpr int kOffIn = kOffOut + 2 * kOutStep;
+constexpr int kEpiBufs = 3;                     // rotating epilogue buffers: residual lands / in-place epilogue / store drains
+constexpr int kOffIn = kOffOut + kEpiBufs * kOutStep;
 constexpr int kOffBar = kOffIn + kInStages * kWinBytes;
 constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignment of the base
 constexpr int kThreads = 576;                   // warp 0 TMA, 1 MMA, 2-9 epilogue, 10-17 producers
@@ -95,6 +96,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box [122 x 64], no swizzle*/,
                    const __grid_constant__ CUtensorMap tmap_w /*[728, 728] box [128 x 64], SW128*/,
                    const __grid_constant__ CUtensorMap tmap_out /*[rows, 728] box [19 x 64], no swizzle*/,
+                   const __grid_constant__ CUtensorMap tmap_res /*[rows, 728] box [40 x 64], no swizzle (residual, padded layout)*/,
                    const SepMidParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -108,8 +110,9 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 2 + s); };  // [2] both CTAs
   auto acc_full = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 4 + t); }; // [3] both CTAs
   auto acc_empty = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 7 + t); };// [3] leader: 16 arrivals
-  const uint32_t tmem_slot = bar0 + 8u * (2 * kWStages + 2 * kInStages + 10);
-  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * (2 * kWStages + 2 * kInStages + 10));
+  auto res_full = [&](int e) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 10 + e); }; // [3] local: residual tiles landed
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kWStages + 2 * kInStages + 13);
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * (2 * kWStages + 2 * kInStages + 13));
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -122,10 +125,11 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < kWStages; ++s) { mbar_init(w_full(s), 2); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < kInStages; ++s) { mbar_init(in_full(s), 1); mbar_init(in_empty(s), kProducerWarps); }
     for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 2 * kProducerWarps); mbar_init(b_empty(s), 1); }
-    for (int t = 0; t < 3; ++t) { mbar_init(acc_full(t), 1); mbar_init(acc_empty(t), 2 * kEpiWarps); }
+    for (int t = 0; t < 3; ++t) { mbar_init(acc_full(t), 1); mbar_init(acc_empty(t), 2 * kEpiWarps); mbar_init(res_full(t), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster_sync_all();
@@ -133,26 +137,35 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // warp-uniform for the compiler
 
   if (warp == 0) {
     // ===================== TMA: input window of this CTA's 80 pixels + its 128 rows of each weight tile =====================
-    if (lane == 0) {
+    // (converged warp, one elected lane issues: TMA instructions take uniform-register operands like tcgen05.mma)
+    {
       int is = 0; uint32_t iph = 0;
       int ws = 0; uint32_t wph = 0;
       for (int li = 0; li < my_items; ++li) {
         const int p0 = (cluster_id + li * num_clusters) * kItemPx;
+#pragma unroll 1
         for (int kb = 0; kb < kNumKb; ++kb) {
           mbar_wait(in_empty(is), iph ^ 1u);
-          mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
-          tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), kb * 64,
-                      p0 + (int)rank * kCtaPx - (kPitch + 1));
+          if (elect_one()) {
+            mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
+            tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), kb * 64,
+                        p0 + (int)rank * kCtaPx - (kPitch + 1));
+          }
+          __syncwarp();
           if (++is == kInStages) { is = 0; iph ^= 1u; }
+#pragma unroll
           for (int ct = 0; ct < 3; ++ct) {
             mbar_wait(w_empty(ws), wph ^ 1u);
-            if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
-            else mbar_arrive_remote(w_full(ws), 0);
-            tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
+            if (elect_one()) {
+              if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
+              else mbar_arrive_remote(w_full(ws), 0);
+              tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
+            }
+            __syncwarp();
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -161,7 +174,6 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA; the whole warp walks the loop, one elected lane issues =====================
     if (is_leader) {
-      if (tmem_base != 0u) __trap();               // all 512 columns are allocated: the base can only be 0 (keeps D addresses immediate)
       const uint32_t idesc = make_idesc(256, kItemPx);
       int ws = 0; uint32_t wph = 0;
       uint32_t q = 0;
@@ -177,7 +189,7 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
             if (kb == 0) mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
             tc_fence_after();
             const uint64_t da = make_smem_desc<128>(smem_base + kOffW + ws * kWBytes);
-            const uint32_t d = (uint32_t)(ct * kItemPx);
+            const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
             if (elect_one()) {
               umma_bf16_2cta(d, da, db, idesc, kb ? 1u : 0u);
               umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
@@ -212,7 +224,29 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       sh[ct] = ok ? __ldg(p.shift + chn[ct]) : 0.f;
     }
     const bool has_res = p.residual != nullptr;
-    uint32_t g = 0;                                   // running step counter: staging buffer = g & 1
+    // Step g (40 pixels x this CTA's 128 channels of one channel tile) works IN PLACE in buffer g % 3: the residual tile of
+    // the step was prefetched there by TMA two steps earlier, the epilogue overwrites it with the output, the leader
+    // stores it and -- once the stores of step g - 1 have drained their buffer -- prefetches the residual of step g + 2
+    // into it.  One 256-thread barrier per step.
+    auto step_coords = [&](uint32_t gg, int& row0, int& col0) {     // global step index -> first row / first channel
+      const uint32_t li2 = gg / 6u, r6 = gg % 6u;
+      row0 = (cluster_id + (int)li2 * num_clusters) * kItemPx + (int)(r6 & 1u) * kStepPx;
+      col0 = (int)(r6 >> 1) * 256 + (int)rank * 128;
+    };
+    const uint32_t total_steps = (uint32_t)my_items * 6u;
+    auto prefetch_res = [&](uint32_t gg) {                          // leader thread only
+      if (gg >= total_steps) return;
+      int row0, col0;
+      step_coords(gg, row0, col0);
+      const uint32_t e = gg % kEpiBufs;
+      mbar_expect_tx(res_full(e), (uint32_t)kOutStep);
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        tma_load_2d(smem_base + kOffOut + e * kOutStep + t * kOutTile, &tmap_res, res_full(e), col0 + (t & 1) * 64,
+                    row0 + (t >> 1) * kCtaPx);
+    };
+    if (leader && has_res) { prefetch_res(0); prefetch_res(1); }
+    uint32_t g = 0;                                   // running step counter
     for (int li = 0; li < my_items; ++li) {
       const int p0 = (cluster_id + li * num_clusters) * kItemPx;
 #pragma unroll
@@ -221,6 +255,7 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
         tc_fence_after();
         for (int s = 0; s < 2; ++s, ++g) {
           const int px0 = hh * kCtaPx + s * kStepPx;          // first pixel (accumulator column) of this warp's 40
+          const uint32_t e = g % kEpiBufs;
           uint32_t v[40];
           {
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + px0);
@@ -238,18 +273,16 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           float f[40];
 #pragma unroll
           for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), sc[ct]), sh[ct]);
-          if (has_res && chn[ct] < kC) {
-            const bf16* rp = p.residual + (size_t)(p0 + px0) * kC + chn[ct];
+          uint8_t* st = smem_gen + kOffOut + e * kOutStep + (hh * 2 + box) * kOutTile + chin * 2;
+          if (has_res) {
+            mbar_wait(res_full(e), (g / kEpiBufs) & 1u);
 #pragma unroll
-            for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(f[j], __bfloat162float(rp[(size_t)j * kC]));
+            for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(f[j], __bfloat162float(*(const bf16*)(st + j * 128)));
           }
           if (p.relu_out) {
 #pragma unroll
             for (int j = 0; j < 40; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (leader) tma_store_wait_read1();                  // the stores of step g - 2 have drained this buffer
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          uint8_t* st = smem_gen + kOffOut + (g & 1u) * kOutStep + (hh * 2 + box) * kOutTile + chin * 2;
 #pragma unroll
           for (int j = 0; j < 40; ++j) *(bf16*)(st + j * 128) = __float2bfloat16_rn(f[j]);
           fence_async_smem();
@@ -264,10 +297,12 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
                 const int y = (row / kPitch) % kPitch;
                 const int col = ct * 256 + (int)rank * 128 + (t & 1) * 64;
                 if (y != kMap && row < p.n_rows && col < kC)
-                  tma_store_2d(&tmap_out, smem_base + kOffOut + (g & 1u) * kOutStep + t * kOutTile + r2 * kPitch * 128, col, row);
+                  tma_store_2d(&tmap_out, smem_base + kOffOut + e * kOutStep + t * kOutTile + r2 * kPitch * 128, col, row);
               }
             }
             tma_store_commit();
+            tma_store_wait_read1();                            // the stores of step g - 1 have drained buffer (g + 2) % 3
+            if (has_res) prefetch_res(g + 2);
           }
         }
       }

@@ -100,9 +100,9 @@ def all_gather_meta(values, group=None, device=None):
         return v
     dev = _collective_device(dist, group, device)
     t = torch.from_numpy(v[0].copy()).to(dev)
-    out = torch.empty((world, v.shape[1]), dtype=torch.int64, device=dev)
+    out = torch.empty(world * v.shape[1], dtype=torch.int64, device=dev)     # flat: gloo requires world * numel
     dist.all_gather_into_tensor(out, t, group=group)
-    return out.cpu().numpy()
+    return out.cpu().numpy().reshape(world, v.shape[1])
 
 
 def all_gather_bytes(buf, sizes, group=None, device=None):
@@ -119,9 +119,9 @@ def all_gather_bytes(buf, sizes, group=None, device=None):
     t = torch.zeros(pad, dtype=torch.uint8, device=dev)
     if buf.shape[0]:
         t[: buf.shape[0]] = torch.from_numpy(buf).to(dev)
-    out = torch.empty((world, pad), dtype=torch.uint8, device=dev)
+    out = torch.empty(world * pad, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(out, t, group=group)
-    host = out.cpu().numpy()
+    host = out.cpu().numpy().reshape(world, pad)
     return [host[r, : sizes[r]] for r in range(world)]
 
 

@@ -91,3 +91,62 @@ def test_single_process_passthrough():
                             [0.0, np.nan, 1.0])
     out = bdist.unpack_groups(bdist.all_gather_groups(msg), np.float32)
     assert list(out["code"]) == [0, 2] and list(out["y_true"]) == [0, 1]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# byte-level collectives behind apply_sharded / detect_sharded (tensor all-gathers, no pickled objects)
+# ----------------------------------------------------------------------------------------------------------------
+def _bytes_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        df = synth.tile_table(n_slides=7, tiles_per_slide=30, seed=5, ragged=True)
+        counts = df.groupby("slide", sort=False).size().to_numpy()
+        lo, hi = bdist.shard_bounds(counts, world)[rank]
+        r0, r1 = int(counts[:lo].sum()), int(counts[:hi].sum())
+        local = df.iloc[r0:r1]
+        if rank == world - 1:                               # the last rank contributes an EMPTY shard of names
+            names = []
+        else:
+            names = list(local["slide"].unique()) + ["slide with spaces \u00e9"]
+        nbuf, nlen = bdist.pack_names(names)
+        meta = bdist.all_gather_meta([len(local), len(names), nbuf.shape[0]])
+        assert meta.shape == (world, 3)
+        tiles = bdist.pack_tiles(local["y_pred"].to_numpy(), local["uncertainty"].to_numpy(), local["y_true"].to_numpy().astype(np.uint8))
+        parts = bdist.all_gather_bytes(tiles, [int(m[0]) * 9 for m in meta])
+        cols = [bdist.unpack_tiles(part, int(m[0]), np.float32) for m, part in zip(meta, parts)]
+        payload = np.concatenate([nlen.view(np.uint8), nbuf])
+        nparts = bdist.all_gather_bytes(payload, [int(m[1]) * 4 + int(m[2]) for m in meta])
+        all_names = []
+        for m, part in zip(meta, nparts):
+            L = int(m[1])
+            all_names += bdist.unpack_names(part[L * 4:], part[:L * 4].copy().view(np.int32))
+        np.savez(os.path.join(out_dir, f"b{rank}.npz"), y_pred=np.concatenate([c[0] for c in cols]),
+                 unc=np.concatenate([c[1] for c in cols]), y_true=np.concatenate([c[2] for c in cols]),
+                 names=np.array(all_names, dtype=object), meta=meta)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_byte_collectives_world2(tmp_path):
+    world = 2
+    mp.spawn(_bytes_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    df = synth.tile_table(n_slides=7, tiles_per_slide=30, seed=5, ragged=True)
+    for r in range(world):
+        g = np.load(tmp_path / f"b{r}.npz", allow_pickle=True)
+        assert g["y_pred"].tobytes() == df["y_pred"].to_numpy().tobytes()          # rank order == table order
+        assert g["unc"].tobytes() == df["uncertainty"].to_numpy().tobytes()
+        assert np.array_equal(g["y_true"], df["y_true"].to_numpy().astype(np.uint8))
+        assert int(g["meta"][:, 0].sum()) == len(df)
+        assert g["names"][-1] == "slide with spaces \u00e9" and len(g["names"]) == int(g["meta"][:, 1].sum())
+
+
+def test_byte_collectives_single_process():
+    nbuf, nlen = bdist.pack_names(["a", "bc", ""])
+    assert bdist.unpack_names(nbuf, nlen) == ["a", "bc", ""]
+    assert bdist.all_gather_meta([3, 4]).tolist() == [[3, 4]]
+    t = bdist.pack_tiles(np.float64([.5, .25]), np.float64([.1, .2]), np.uint8([1, 0]))
+    assert t.shape[0] == 2 * 17
+    yp, un, yt = bdist.unpack_tiles(bdist.all_gather_bytes(t, [t.shape[0]])[0], 2, np.float64)
+    assert yp.tolist() == [.5, .25] and un.tolist() == [.1, .2] and yt.tolist() == [1, 0]
