@@ -58,6 +58,11 @@ constexpr int kBNMax = 256;     // UMMA N max
 constexpr int kThreads = 192;   // 6 warps
 constexpr int kAccStages = 2;
 
+// Wait used by roles that idle for a long time (epilogue warps waiting for a whole item's accumulation): after the first
+// hardware-suspended try the retry loop backs off with nanosleep.  ncu: without it the idle epilogue warps of the fused
+// middle-flow kernel re-polled every ~60 cycles and issued 22 % of ALL instructions of the kernel.
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, uint32_t sleep_ns);
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -88,6 +93,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > 4000000u) {        // each failed try_wait parks the thread for up to the hint: this is seconds
+      printf("bq: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++spins > 40000000u) {
       printf("bq: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }

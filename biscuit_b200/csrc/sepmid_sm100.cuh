@@ -22,7 +22,7 @@
 //
 // Work item = 160 consecutive padded rows (8 padded image rows) per CTA pair; per 64-channel k-block and CTA:
 //   warp 0        TMA: the (80 + 42)-row input window of this CTA's 80 pixels, and three 128 x 64 weight tiles
-//   warps 10-17   depthwise producers: thread = (4 channels, 5 consecutive pixels), the three row triplets slide in
+//   warps 10-19   depthwise producers: thread = (4 channels, 4 consecutive pixels), the three row triplets slide in
 //                 registers (3 LDS.64 + 18 FFMA2 per output, same tap order as depthwise3x3_pipe_kernel) -> bf16 ->
 //                 this CTA's half of the 128B-swizzled N-side stage
 //   warp 1        (leader CTA) 3 x 4 tcgen05.mma.cta_group::2 (M = 256, N = 160, K = 16) per k-block
@@ -49,14 +49,21 @@ constexpr int kCtaPx = 80;                      // rows produced per CTA
 constexpr int kWinRows = kCtaPx + 2 * (kPitch + 1);   // 122: halo of 21 rows on either side
 constexpr int kWinBytes = kWinRows * 128;       // 15,616
 constexpr int kNumKb = 12;                      // ceil(728 / 64); the last k-block holds 24 channels (2 k-steps)
-constexpr int kWStages = 6;
-constexpr int kWBytes = 128 * 128;              // 128 weight rows x 64 k
+#ifndef BQ_SM_WST
+#define BQ_SM_WST 2          // weight ring depth in K-BLOCKS (a stage = the three 128 x 64 tiles of one k-block, 48 KB)
+#endif
+#ifndef BQ_SM_BST
+#define BQ_SM_BST 2
+#endif
+constexpr int kWStages = BQ_SM_WST;
+constexpr int kWTile = 128 * 128;               // 128 weight rows x 64 k
+constexpr int kWBytes = 3 * kWTile;             // one ring stage: the three channel tiles of a k-block
 constexpr int kInStages = 3;
-constexpr int kBStages = 2;
+constexpr int kBStages = BQ_SM_BST;
 constexpr int kBBytes = kCtaPx * 128;           // 10,240 (multiple of 1024)
 constexpr int kStepPx = 40;                     // epilogue step: 40 pixels x 128 channels per CTA
-constexpr int kOutTile = kStepPx * 128;         // [40 px][64 ch] bf16
-constexpr int kOutStep = 4 * kOutTile;          // tiles (pixel half, channel box)
+constexpr int kOutTile = kStepPx * 64;          // one epilogue warp's tile of a step: [40 px][32 ch] bf16
+constexpr int kOutStep = 8 * kOutTile;          // the eight epilogue warps
 constexpr int kOffW = 0;
 constexpr int kOffB = kOffW + kWStages * kWBytes;
 constexpr int kOffOut = kOffB + kBStages * kBBytes;
@@ -64,8 +71,22 @@ constexpr int kEpiBufs = 3;                     // rotating epilogue buffers: re
 constexpr int kOffIn = kOffOut + kEpiBufs * kOutStep;
 constexpr int kOffBar = kOffIn + kInStages * kWinBytes;
 constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignment of the base
-constexpr int kThreads = 576;                   // warp 0 TMA, 1 MMA, 2-9 epilogue, 10-17 producers
-constexpr int kProducerWarps = 8;
+// developer tunables (profiles/build_variants.py builds A/B copies of the library with -D overrides)
+#ifndef BQ_SM_PW
+#define BQ_SM_PW 8             // producer warps: 8 (5-pixel strips) or 10 (4-pixel strips)
+#endif
+#ifndef BQ_SM_SWPIPE
+#define BQ_SM_SWPIPE 0         // explicit software pipelining of the window loads + tap prefetch in the producers
+#endif
+#ifndef BQ_SM_EPI_V2
+#define BQ_SM_EPI_V2 1         // epilogue on accumulator fragments (tcgen05.ld.16x256b + stmatrix.trans) instead of one lane per channel
+#endif
+#ifndef BQ_SM_EARLY
+#define BQ_SM_EARLY 1          // epilogue hands a channel tile back before its first staging store
+#endif
+constexpr int kProducerWarps = BQ_SM_PW;
+constexpr int kThreads = 32 * (2 + 8 + kProducerWarps);   // warp 0 TMA, 1 MMA, 2-9 epilogue, 10.. producers (registers are granted per 4 warps: 18 cost as 20)
+constexpr int kStripPx = kCtaPx / (kProducerWarps * 2);   // 16 channel groups x 20 strips of 4 consecutive pixels
 constexpr int kEpiWarps = 8;
 constexpr int kSlackRows = 2 * kItemPx;         // rows allocated past the last image (the last item may overhang)
 
@@ -91,28 +112,75 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 16 TMEM lanes x 256 bits: thread t gets (lane t/4, columns 2(t%4), 2(t%4)+1) in r0, r1 and (lane t/4 + 8, same columns) in
+// r2, r3 -- the m16n8 accumulator-fragment layout, repeated along the columns for .x4 (registers 4i.. = columns 8i..).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+// four 8x8 b16 matrices, transposed on the way to / from shared memory: thread i supplies the address of row i % 8 of
+// matrix i / 8; register k of thread t holds elements (row t/4, columns 2(t%4), 2(t%4)+1) of matrix k BEFORE the transpose
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
+  uint32_t r;
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 template <bool RELU_IN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box [122 x 64], no swizzle*/,
                    const __grid_constant__ CUtensorMap tmap_w /*[728, 728] box [128 x 64], SW128*/,
-                   const __grid_constant__ CUtensorMap tmap_out /*[rows, 728] box [19 x 64], no swizzle*/,
-                   const __grid_constant__ CUtensorMap tmap_res /*[rows, 728] box [40 x 64], no swizzle (residual, padded layout)*/,
+                   const __grid_constant__ CUtensorMap tmap_out /*[rows, 728] box [19 x 32], no swizzle*/,
+                   const __grid_constant__ CUtensorMap tmap_res /*[rows, 728] box [40 x 32], no swizzle (residual, padded layout)*/,
                    const SepMidParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar0 = smem_base + kOffBar;
-  auto w_full = [&](int s) { return bar0 + 8u * s; };                          // [6]  leader: 2 arrivals + tx
-  auto w_empty = [&](int s) { return bar0 + 8u * (kWStages + s); };            // [6]  both CTAs, multicast commit
-  auto in_full = [&](int s) { return bar0 + 8u * (2 * kWStages + s); };        // [3]  local
-  auto in_empty = [&](int s) { return bar0 + 8u * (2 * kWStages + kInStages + s); };
-  auto b_full = [&](int s) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + s); };       // [2] leader: 16 arrivals
-  auto b_empty = [&](int s) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 2 + s); };  // [2] both CTAs
-  auto acc_full = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 4 + t); }; // [3] both CTAs
-  auto acc_empty = [&](int t) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 7 + t); };// [3] leader: 16 arrivals
-  auto res_full = [&](int e) { return bar0 + 8u * (2 * kWStages + 2 * kInStages + 10 + e); }; // [3] local: residual tiles landed
-  const uint32_t tmem_slot = bar0 + 8u * (2 * kWStages + 2 * kInStages + 13);
-  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * (2 * kWStages + 2 * kInStages + 13));
+  constexpr int oWE = kWStages, oIF = 2 * kWStages, oIE = oIF + kInStages, oBF = oIE + kInStages, oBE = oBF + kBStages,
+                oAF = oBE + kBStages, oAE = oAF + 3, oRF = oAE + 3, oTM = oRF + 8 * kEpiBufs;
+  static_assert(8 * (oTM + 1) <= 512, "barrier area");
+  auto w_full = [&](int s) { return bar0 + 8u * s; };                  // leader: 2 arrivals + tx
+  auto w_empty = [&](int s) { return bar0 + 8u * (oWE + s); };         // both CTAs, multicast commit
+  auto in_full = [&](int s) { return bar0 + 8u * (oIF + s); };         // local
+  auto in_empty = [&](int s) { return bar0 + 8u * (oIE + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (oBF + s); };          // leader: 2 x producer-warp arrivals
+  auto b_empty = [&](int s) { return bar0 + 8u * (oBE + s); };         // both CTAs
+  auto acc_full = [&](int t) { return bar0 + 8u * (oAF + t); };        // both CTAs
+  auto acc_empty = [&](int t) { return bar0 + 8u * (oAE + t); };       // leader: 2 x epilogue-warp arrivals
+  auto res_full = [&](int w8, int e) { return bar0 + 8u * (oRF + w8 * kEpiBufs + e); };   // local, per epilogue warp: residual tile landed
+  const uint32_t tmem_slot = bar0 + 8u * oTM;
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + kOffBar + 8 * oTM);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -129,7 +197,9 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     for (int s = 0; s < kWStages; ++s) { mbar_init(w_full(s), 2); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < kInStages; ++s) { mbar_init(in_full(s), 1); mbar_init(in_empty(s), kProducerWarps); }
     for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 2 * kProducerWarps); mbar_init(b_empty(s), 1); }
-    for (int t = 0; t < 3; ++t) { mbar_init(acc_full(t), 1); mbar_init(acc_empty(t), 2 * kEpiWarps); mbar_init(res_full(t), 1); }
+    for (int t = 0; t < 3; ++t) { mbar_init(acc_full(t), 1); mbar_init(acc_empty(t), 2 * kEpiWarps); }
+    for (int w8 = 0; w8 < kEpiWarps; ++w8)
+      for (int e = 0; e < kEpiBufs; ++e) mbar_init(res_full(w8, e), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster_sync_all();
@@ -151,23 +221,32 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
         for (int kb = 0; kb < kNumKb; ++kb) {
           mbar_wait(in_empty(is), iph ^ 1u);
           if (elect_one()) {
+#ifdef BQ_SM_DIAG_NOWIN       // TIMING DIAGNOSTIC ONLY (wrong results): no input-window traffic
+            mbar_arrive(in_full(is));
+#else
             mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
             tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), kb * 64,
                         p0 + (int)rank * kCtaPx - (kPitch + 1));
+#endif
           }
           __syncwarp();
           if (++is == kInStages) { is = 0; iph ^= 1u; }
+          mbar_wait(w_empty(ws), wph ^ 1u);
+          if (elect_one()) {
+#ifdef BQ_SM_DIAG_W1          // TIMING DIAGNOSTIC ONLY (wrong results): fetch one of the three weight tiles per k-block
+            if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWTile);
+            else mbar_arrive_remote(w_full(ws), 0);
+            for (int ct = 0; ct < 1; ++ct)
+#else
+            if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
+            else mbar_arrive_remote(w_full(ws), 0);
 #pragma unroll
-          for (int ct = 0; ct < 3; ++ct) {
-            mbar_wait(w_empty(ws), wph ^ 1u);
-            if (elect_one()) {
-              if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
-              else mbar_arrive_remote(w_full(ws), 0);
-              tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
-            }
-            __syncwarp();
-            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+            for (int ct = 0; ct < 3; ++ct)
+#endif
+              tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes + ct * kWTile, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
           }
+          __syncwarp();
+          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
         }
       }
     }
@@ -176,44 +255,68 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     if (is_leader) {
       const uint32_t idesc = make_idesc(256, kItemPx);
       int ws = 0; uint32_t wph = 0;
-      uint32_t q = 0;
+      int bs = 0; uint32_t bph = 0;
       for (int li = 0; li < my_items; ++li) {
 #pragma unroll 1
-        for (int kb = 0; kb < kNumKb; ++kb, ++q) {
-          const int bs = (int)(q & 1u);
-          mbar_wait(b_full(bs), (q >> 1) & 1u);
+        for (int kb = 0; kb < kNumKb; ++kb) {
+          mbar_wait(b_full(bs), bph);
+          mbar_wait(w_full(ws), wph);
+          tc_fence_after();
           const uint64_t db = make_smem_desc<128>(smem_base + kOffB + bs * kBBytes);
+          const uint64_t da0 = make_smem_desc<128>(smem_base + kOffW + ws * kWBytes);
+          if (kb == 0) {
+            // first k-block of an item: each channel tile starts as soon as the epilogue has handed IT back
 #pragma unroll
-          for (int ct = 0; ct < 3; ++ct) {
-            mbar_wait(w_full(ws), wph);
-            if (kb == 0) mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
-            tc_fence_after();
-            const uint64_t da = make_smem_desc<128>(smem_base + kOffW + ws * kWBytes);
-            const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
-            if (elect_one()) {
-              umma_bf16_2cta(d, da, db, idesc, kb ? 1u : 0u);
-              umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
-              if (kb != kNumKb - 1) {              // the last k-block holds 24 channels: two k-steps
+            for (int ct = 0; ct < 3; ++ct) {
+              mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
+              tc_fence_after();
+              const uint64_t da = da0 + (uint64_t)(ct * (kWTile >> 4));
+              const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
+              if (elect_one()) {
+                umma_bf16_2cta(d, da, db, idesc, 0u);
+                umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
                 umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
                 umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
+                if (ct == 2) { umma_commit_2cta(w_empty(ws)); umma_commit_2cta(b_empty(bs)); }
+              }
+              __syncwarp();
+            }
+          } else {
+            if (elect_one()) {
+#pragma unroll
+              for (int ct = 0; ct < 3; ++ct) {
+                const uint64_t da = da0 + (uint64_t)(ct * (kWTile >> 4));
+                const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
+                umma_bf16_2cta(d, da, db, idesc, 1u);
+                umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
+                if (kb != kNumKb - 1) {              // the last k-block holds 24 channels: two k-steps
+                  umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
+                  umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
+                } else {
+                  umma_commit_2cta(acc_full(ct));
+                }
               }
               umma_commit_2cta(w_empty(ws));
-              if (kb == kNumKb - 1) umma_commit_2cta(acc_full(ct));
-              if (ct == 2) umma_commit_2cta(b_empty(bs));
+              umma_commit_2cta(b_empty(bs));
             }
             __syncwarp();
-            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
+          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          if (++bs == kBStages) { bs = 0; bph ^= 1u; }
         }
       }
     }
   } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue: 128 channels (TMEM lanes) x 160 pixels (columns) per channel tile =====================
+    // Eight INDEPENDENT warp pipelines (no block-level barrier, no single store leader): warp = (TMEM lane quadrant: 32
+    // channels, pixel half: 80 columns).  A step = this warp's [40 px][32 ch] tile, finished IN PLACE in the warp's
+    // buffer step % 3: the residual tile of the step was prefetched there by this warp's own TMA load, the lanes
+    // overwrite it with the output, one elected lane stores it (one 19-pixel box per image row) and refills the buffer
+    // whose stores have drained.  ncu / timing diagnostics: with a 256-thread barrier and one leader issuing all stores
+    // per step the epilogue cost 1/3 of the kernel (the next item's MMAs wait for the channel tiles to be handed back).
     const int quad = warp & 3;                        // TMEM lane quadrant -> channels quad*32 .. +31 of this CTA's 128
     const int hh = (warp - 2) >> 2;                   // pixel half: columns hh*80 .. +79
-    const bool leader = (warp == 2 && lane == 0);
-    const int chin = (quad & 1) * 32 + lane;          // channel inside the 64-channel store box
-    const int box = quad >> 1;
+    const int w8 = warp - 2;
     float sc[3], sh[3];
     int chn[3];
 #pragma unroll
@@ -224,95 +327,208 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       sh[ct] = ok ? __ldg(p.shift + chn[ct]) : 0.f;
     }
     const bool has_res = p.residual != nullptr;
-    // Step g (40 pixels x this CTA's 128 channels of one channel tile) works IN PLACE in buffer g % 3: the residual tile of
-    // the step was prefetched there by TMA two steps earlier, the epilogue overwrites it with the output, the leader
-    // stores it and -- once the stores of step g - 1 have drained their buffer -- prefetches the residual of step g + 2
-    // into it.  One 256-thread barrier per step.
-    auto step_coords = [&](uint32_t gg, int& row0, int& col0) {     // global step index -> first row / first channel
-      const uint32_t li2 = gg / 6u, r6 = gg % 6u;
-      row0 = (cluster_id + (int)li2 * num_clusters) * kItemPx + (int)(r6 & 1u) * kStepPx;
-      col0 = (int)(r6 >> 1) * 256 + (int)rank * 128;
-    };
     const uint32_t total_steps = (uint32_t)my_items * 6u;
-    auto prefetch_res = [&](uint32_t gg) {                          // leader thread only
+    const uint32_t my_out = smem_base + kOffOut + w8 * (kEpiBufs * kOutTile);
+    uint8_t* my_out_gen = smem_gen + kOffOut + w8 * (kEpiBufs * kOutTile);
+    auto step_coords = [&](uint32_t gg, int& row0, int& col0) {     // warp-local step index -> first row / first channel
+      const uint32_t li2 = gg / 6u, r6 = gg % 6u;
+      row0 = (cluster_id + (int)li2 * num_clusters) * kItemPx + hh * kCtaPx + (int)(r6 & 1u) * kStepPx;
+      col0 = (int)(r6 >> 1) * 256 + (int)rank * 128 + quad * 32;
+    };
+    auto prefetch_res = [&](uint32_t gg) {                          // one elected lane
       if (gg >= total_steps) return;
       int row0, col0;
       step_coords(gg, row0, col0);
       const uint32_t e = gg % kEpiBufs;
-      mbar_expect_tx(res_full(e), (uint32_t)kOutStep);
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        tma_load_2d(smem_base + kOffOut + e * kOutStep + t * kOutTile, &tmap_res, res_full(e), col0 + (t & 1) * 64,
-                    row0 + (t >> 1) * kCtaPx);
+      mbar_expect_tx(res_full(w8, e), (uint32_t)kOutTile);
+      tma_load_2d(my_out + e * kOutTile, &tmap_res, res_full(w8, e), col0, row0);
     };
-    if (leader && has_res) { prefetch_res(0); prefetch_res(1); }
-    uint32_t g = 0;                                   // running step counter
+    if (has_res && elect_one()) { prefetch_res(0); prefetch_res(1); }
+    __syncwarp();
+    uint32_t g = 0;                                   // running step counter of this warp
     for (int li = 0; li < my_items; ++li) {
-      const int p0 = (cluster_id + li * num_clusters) * kItemPx;
 #pragma unroll
       for (int ct = 0; ct < 3; ++ct) {
         mbar_wait(acc_full(ct), (uint32_t)li & 1u);
         tc_fence_after();
-        for (int s = 0; s < 2; ++s, ++g) {
-          const int px0 = hh * kCtaPx + s * kStepPx;          // first pixel (accumulator column) of this warp's 40
-          const uint32_t e = g % kEpiBufs;
-          uint32_t v[40];
-          {
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + px0);
-            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-            uint32_t (&v1)[8] = *reinterpret_cast<uint32_t (*)[8]>(&v[32]);
-            tmem_ld_32x32b_x32(t_addr, v0);
-            tmem_ld_32x32b_x8(t_addr + 32u, v1);
-            tmem_ld_wait();
-          }
-          if (s == 1) {                                        // this warp has read its share of channel tile ct
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
-          }
-          float f[40];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + hh * kCtaPx);
+        uint32_t pk[20];
+        auto load40 = [&](uint32_t col, uint32_t (&v)[40]) {
+          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&v1)[8] = *reinterpret_cast<uint32_t (*)[8]>(&v[32]);
+          tmem_ld_32x32b_x32(t_addr + col, v0);
+          tmem_ld_32x32b_x8(t_addr + col + 32u, v1);
+          tmem_ld_wait();
+        };
+        auto finish = [&](const uint32_t (&v)[40], uint32_t gg) {          // -> pk[]: bf16 pairs (pixel j, j + 1)
+          const uint32_t e = gg % kEpiBufs;
+          const uint8_t* st = my_out_gen + e * kOutTile + lane * 2;
+          if (has_res) mbar_wait(res_full(w8, e), (gg / kEpiBufs) & 1u);
 #pragma unroll
-          for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), sc[ct]), sh[ct]);
-          uint8_t* st = smem_gen + kOffOut + e * kOutStep + (hh * 2 + box) * kOutTile + chin * 2;
-          if (has_res) {
-            mbar_wait(res_full(e), (g / kEpiBufs) & 1u);
-#pragma unroll
-            for (int j = 0; j < 40; ++j) f[j] = __fadd_rn(f[j], __bfloat162float(*(const bf16*)(st + j * 128)));
+          for (int j = 0; j < 40; j += 2) {
+            float f0 = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), sc[ct]), sh[ct]);
+            float f1 = __fadd_rn(__fmul_rn(__uint_as_float(v[j + 1]), sc[ct]), sh[ct]);
+            if (has_res) {
+              f0 = __fadd_rn(f0, __bfloat162float(*(const bf16*)(st + j * 64)));
+              f1 = __fadd_rn(f1, __bfloat162float(*(const bf16*)(st + (j + 1) * 64)));
+            }
+            if (p.relu_out) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            const __nv_bfloat162 b = __floats2bfloat162_rn(f0, f1);
+            pk[j >> 1] = *(const uint32_t*)&b;
           }
-          if (p.relu_out) {
+        };
+        auto store_step = [&](uint32_t gg) {
+          const uint32_t e = gg % kEpiBufs;
+          uint8_t* st = my_out_gen + e * kOutTile + lane * 2;
 #pragma unroll
-            for (int j = 0; j < 40; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 40; j += 2) {
+            *(uint16_t*)(st + j * 64) = (uint16_t)(pk[j >> 1] & 0xFFFFu);
+            *(uint16_t*)(st + (j + 1) * 64) = (uint16_t)(pk[j >> 1] >> 16);
           }
-#pragma unroll
-          for (int j = 0; j < 40; ++j) *(bf16*)(st + j * 128) = __float2bfloat16_rn(f[j]);
           fence_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (leader) {
-            // one box of 19 valid pixels per image row; zero rows (y == 19) and rows past the batch are skipped
+          __syncwarp();
+          if (elect_one()) {
+            int row0, col0;
+            step_coords(gg, row0, col0);
+            // one box of 19 valid pixels per image row; zero rows (y == 19), rows past the batch and channels >= 728 are skipped
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-#pragma unroll
-              for (int r2 = 0; r2 < 2; ++r2) {
-                const int row = p0 + (t >> 1) * kCtaPx + s * kStepPx + r2 * kPitch;
-                const int y = (row / kPitch) % kPitch;
-                const int col = ct * 256 + (int)rank * 128 + (t & 1) * 64;
-                if (y != kMap && row < p.n_rows && col < kC)
-                  tma_store_2d(&tmap_out, smem_base + kOffOut + e * kOutStep + t * kOutTile + r2 * kPitch * 128, col, row);
-              }
+            for (int r2 = 0; r2 < 2; ++r2) {
+              const int row = row0 + r2 * kPitch;
+              const int y = (row / kPitch) % kPitch;
+              if (y != kMap && row < p.n_rows && col0 < kC)
+                tma_store_2d(&tmap_out, my_out + e * kOutTile + r2 * kPitch * 64, col0, row);
             }
             tma_store_commit();
-            tma_store_wait_read1();                            // the stores of step g - 1 have drained buffer (g + 2) % 3
-            if (has_res) prefetch_res(g + 2);
+            tma_store_wait_read1();                            // this warp's stores of step gg - 1 have drained buffer (gg + 2) % 3
+            if (has_res) prefetch_res(gg + 2);
           }
+          __syncwarp();
+        };
+#ifdef BQ_SM_DIAG_NOEPI          // TIMING DIAGNOSTIC ONLY: the epilogue only hands the tile back
+        if (true) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
+          g += 2;
+        } else
+#endif
+#if BQ_SM_EPI_V2
+        if (true) {
+          // Fragment epilogue.  Thread t holds channels cq = t/4 + {0, 8, 16, 24} of the warp's 32 and pixel pairs
+          // 2(t%4) of every 8-pixel block: BN constants are four per channel tile, a pixel pair packs into one bf16x2
+          // register (cvt.rn.relu fuses the ReLU), and ONE stmatrix.x4.trans writes an [8 px][32 ch] block of the
+          // staging tile (64-byte rows, 16-byte chunks XOR-swizzled with (row >> 1) & 3 == TMA SWIZZLE_64B).
+          float s4[4], h4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = ct * 256 + (int)rank * 128 + quad * 32 + (lane >> 2) + 8 * k;
+            s4[k] = c < kC ? __ldg(p.scale + c) : 0.f;
+            h4[k] = c < kC ? __ldg(p.shift + c) : 0.f;
+          }
+          const uint32_t t_lo = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + hh * kCtaPx);
+          const uint32_t t_hi = t_lo + (16u << 16);
+          const int mrow = lane & 7, mmat = lane >> 3;             // this lane's row address duty for ld/stmatrix
+          uint32_t pkv[20];
+          auto load_step = [&](int s2, uint32_t (&lo)[20], uint32_t (&hi)[20]) {
+            const uint32_t col = (uint32_t)(s2 * kStepPx);
+            tmem_ld_16x256b_x4(t_lo + col, &lo[0]);
+            tmem_ld_16x256b_x1(t_lo + col + 32u, &lo[16]);
+            tmem_ld_16x256b_x4(t_hi + col, &hi[0]);
+            tmem_ld_16x256b_x1(t_hi + col + 32u, &hi[16]);
+            tmem_ld_wait();
+          };
+          auto finish2 = [&](const uint32_t (&lo)[20], const uint32_t (&hi)[20], uint32_t gg) {
+            const uint32_t e = gg % kEpiBufs;
+            if (has_res) mbar_wait(res_full(w8, e), (gg / kEpiBufs) & 1u);
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                f[2 * k] = __fadd_rn(__fmul_rn(__uint_as_float(lo[4 * b + 2 * k]), s4[k]), h4[k]);
+                f[2 * k + 1] = __fadd_rn(__fmul_rn(__uint_as_float(lo[4 * b + 2 * k + 1]), s4[k]), h4[k]);
+                f[4 + 2 * k] = __fadd_rn(__fmul_rn(__uint_as_float(hi[4 * b + 2 * k]), s4[2 + k]), h4[2 + k]);
+                f[4 + 2 * k + 1] = __fadd_rn(__fmul_rn(__uint_as_float(hi[4 * b + 2 * k + 1]), s4[2 + k]), h4[2 + k]);
+              }
+              if (has_res) {
+                const int r = 8 * b + mrow;
+                uint32_t q0, q1, q2, q3;
+                ldmatrix_x4_trans(my_out + e * kOutTile + r * 64 + ((mmat ^ ((r >> 1) & 3)) << 4), q0, q1, q2, q3);
+                const uint32_t qq[4] = {q0, q1, q2, q3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  f[2 * k] = __fadd_rn(f[2 * k], __uint_as_float(qq[k] << 16));
+                  f[2 * k + 1] = __fadd_rn(f[2 * k + 1], __uint_as_float(qq[k] & 0xFFFF0000u));
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pkv[4 * b + k] = pack_bf16x2(f[2 * k], f[2 * k + 1], p.relu_out != 0);
+            }
+          };
+          auto store_step2 = [&](uint32_t gg) {
+            const uint32_t e = gg % kEpiBufs;
+            if (has_res) __syncwarp();                           // every lane's ldmatrix of this buffer precedes the overwrite
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+              const int r = 8 * b + mrow;
+              stmatrix_x4_trans(my_out + e * kOutTile + r * 64 + ((mmat ^ ((r >> 1) & 3)) << 4), pkv[4 * b], pkv[4 * b + 1],
+                                pkv[4 * b + 2], pkv[4 * b + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              int row0, col0;
+              step_coords(gg, row0, col0);
+#pragma unroll
+              for (int r2 = 0; r2 < 2; ++r2) {
+                const int row = row0 + r2 * kPitch;
+                const int y = (row / kPitch) % kPitch;
+                if (y != kMap && row < p.n_rows && col0 < kC)
+                  tma_store_2d(&tmap_out, my_out + e * kOutTile + r2 * kPitch * 64, col0, row);
+              }
+              tma_store_commit();
+              tma_store_wait_read1();
+              if (has_res) prefetch_res(gg + 2);
+            }
+            __syncwarp();
+          };
+          uint32_t lo[20], hi[20];
+          load_step(0, lo, hi);
+          finish2(lo, hi, g);
+          if (!BQ_SM_EARLY) store_step2(g);
+          load_step(1, lo, hi);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
+          if (BQ_SM_EARLY) store_step2(g);
+          finish2(lo, hi, g + 1);
+          store_step2(g + 1);
+          g += 2;
+        } else
+#endif
+        {
+          uint32_t v[40];
+          load40(0u, v);
+          finish(v, g);
+          if (!BQ_SM_EARLY) store_step(g);
+          load40((uint32_t)kStepPx, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
+          if (BQ_SM_EARLY) store_step(g);
+          finish(v, g + 1);
+          store_step(g + 1);
+          g += 2;
         }
       }
     }
-    if (leader) tma_store_wait_all();
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
   } else {
     // ===================== depthwise producers =====================
     const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
-    const int c4 = ptid & 15, strip = ptid >> 4;               // 4 channels x 5 consecutive pixels
-    const int b0 = strip * 5;
+    const int c4 = ptid & 15, strip = ptid >> 4;               // 4 channels x kStripPx consecutive pixels
+    const int b0 = strip * kStripPx;
     auto ld = [&](const uint8_t* rowp, float2 (&d)[2]) {
       uint2 raw = *(const uint2*)rowp;
       if (RELU_IN) {
@@ -325,13 +541,20 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       d[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
     };
     const uint32_t total_kb = (uint32_t)my_items * kNumKb;
-    for (uint32_t q = 0; q < total_kb; ++q) {
-      const int kb = (int)(q % kNumKb);
-      const int is = (int)(q % kInStages), bs = (int)(q & 1u);
-      const uint32_t iph = (q / kInStages) & 1u, bph = (q >> 1) & 1u;
+    // raw (bf16-pair) window loads; unpacked on use, so a row fetched one output ahead costs two registers, not four
+    auto ldraw = [&](const uint8_t* rowp) { return *(const uint2*)rowp; };
+    auto unpack = [&](uint2 raw, float2 (&d)[2]) {
+      if (RELU_IN) {
+        const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+        __nv_bfloat162* hb = (__nv_bfloat162*)&raw;
+        hb[0] = __hmax2(hb[0], z2);
+        hb[1] = __hmax2(hb[1], z2);
+      }
+      d[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
+      d[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+    };
+    auto load_w = [&](int kb, float2 (&w)[9][2]) {
       const int c = kb * 64 + c4 * 4;
-      const bool live = c < kC + 8;                            // the last k-block feeds 2 k-steps (channels 704..735)
-      float2 w[9][2];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -339,22 +562,42 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
         w[t][0] = make_float2(wv.x, wv.y);
         w[t][1] = make_float2(wv.z, wv.w);
       }
+    };
+    float2 w[9][2];
+    if (BQ_SM_SWPIPE && total_kb) load_w(0, w);
+    for (uint32_t q = 0; q < total_kb; ++q) {
+      const int kb = (int)(q % kNumKb);
+      const int is = (int)(q % kInStages), bs = (int)(q % kBStages);
+      const uint32_t iph = (q / kInStages) & 1u, bph = (q / kBStages) & 1u;
+      const bool live = kb * 64 + c4 * 4 < kC + 8;             // the last k-block feeds 2 k-steps (channels 704..735)
+      if (!BQ_SM_SWPIPE) load_w(kb, w);
       mbar_wait(in_full(is), iph);
       mbar_wait(b_empty(bs), bph ^ 1u);
+#ifdef BQ_SM_DIAG_NOPROD        // TIMING DIAGNOSTIC ONLY: producers skip the depthwise math
+      if (false) {
+#else
       if (live) {
+#endif
         // window row of output pixel o, tap (dy, dx): o + 21 + dy*20 + dx  ->  top o+{0,1,2}, mid o+{20,21,22}, bottom o+{40,41,42}
         const uint8_t* win = smem_gen + kOffIn + is * kWinBytes + (size_t)b0 * 128 + c4 * 8;
         uint8_t* bdst = smem_gen + kOffB + bs * kBBytes;
         float2 tp[3][2], md[3][2], bt[3][2];
-        ld(win, tp[0]); ld(win + 128, tp[1]);
-        ld(win + 20 * 128, md[0]); ld(win + 21 * 128, md[1]);
-        ld(win + 40 * 128, bt[0]); ld(win + 41 * 128, bt[1]);
+        {
+          const uint2 r0 = ldraw(win), r1 = ldraw(win + 128), r2 = ldraw(win + 20 * 128), r3 = ldraw(win + 21 * 128);
+          const uint2 r4 = ldraw(win + 40 * 128), r5 = ldraw(win + 41 * 128);
+          unpack(r0, tp[0]); unpack(r1, tp[1]); unpack(r2, md[0]); unpack(r3, md[1]); unpack(r4, bt[0]); unpack(r5, bt[1]);
+        }
+        uint2 nt = ldraw(win + 2 * 128), nm = ldraw(win + 22 * 128), nb2 = ldraw(win + 42 * 128);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < kStripPx; ++i) {
           const int i0 = i % 3, i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-          ld(win + (size_t)(i + 2) * 128, tp[i2]);
-          ld(win + (size_t)(i + 22) * 128, md[i2]);
-          ld(win + (size_t)(i + 42) * 128, bt[i2]);
+          unpack(nt, tp[i2]); unpack(nm, md[i2]); unpack(nb2, bt[i2]);
+          if (BQ_SM_SWPIPE && i < kStripPx - 1) {       // the rows of the NEXT output are requested before this output's math (and before its store:
+                             // the compiler will not hoist a shared load above a shared store it cannot disambiguate)
+            nt = ldraw(win + (size_t)(i + 3) * 128);
+            nm = ldraw(win + (size_t)(i + 23) * 128);
+            nb2 = ldraw(win + (size_t)(i + 43) * 128);
+          }
           float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
           a0 = __ffma2_rn(tp[i0][0], w[0][0], a0); a1 = __ffma2_rn(tp[i0][1], w[0][1], a1);
           a0 = __ffma2_rn(tp[i1][0], w[1][0], a0); a1 = __ffma2_rn(tp[i1][1], w[1][1], a1);
@@ -365,6 +608,11 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           a0 = __ffma2_rn(bt[i0][0], w[6][0], a0); a1 = __ffma2_rn(bt[i0][1], w[6][1], a1);
           a0 = __ffma2_rn(bt[i1][0], w[7][0], a0); a1 = __ffma2_rn(bt[i1][1], w[7][1], a1);
           a0 = __ffma2_rn(bt[i2][0], w[8][0], a0); a1 = __ffma2_rn(bt[i2][1], w[8][1], a1);
+          if (!BQ_SM_SWPIPE && i < kStripPx - 1) {
+            nt = ldraw(win + (size_t)(i + 3) * 128);
+            nm = ldraw(win + (size_t)(i + 23) * 128);
+            nb2 = ldraw(win + (size_t)(i + 43) * 128);
+          }
           const int pr = b0 + i;
           uint2 o;
           __nv_bfloat162* ob = (__nv_bfloat162*)&o;
@@ -373,6 +621,8 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           *(uint2*)(bdst + (size_t)pr * 128 + (((c4 >> 1) ^ (pr & 7)) << 4) + (c4 & 1) * 8) = o;
         }
       }
+      // the next k-block's taps are requested now: their L2 latency hides behind the fence, the arrives and the next waits
+      if (BQ_SM_SWPIPE && q + 1 < total_kb) load_w((int)((q + 1) % kNumKb), w);
       fence_async_smem();           // generic smem writes -> async proxy (tensor core), and window reads -> next TMA fill
       __syncwarp();
       if (lane == 0) {
