@@ -294,7 +294,7 @@ def run_native_arm(args, rank, world, local_rank):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(fam, {}).get("dram_bytes_per_launch")
-    tensor_bound = fam.startswith("gemm") or fam == "head_gemm"
+    tensor_bound = fam.startswith("gemm") or fam in ("head_gemm", "sepconv_mid")
     if tensor_bound:
         achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         roof = {"kernel": fam, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"],

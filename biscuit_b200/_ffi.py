@@ -33,7 +33,7 @@ class RocResult(C.Structure):
 class ModelConfig(C.Structure):
     _fields_ = [("tile_px", C.c_int32), ("hidden_width", C.c_int32), ("hidden_layers", C.c_int32),
                 ("n_classes", C.c_int32), ("dropout", C.c_float), ("max_batch", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("dropout_sites", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class NamedTensor(C.Structure):

@@ -39,9 +39,12 @@ struct HeadParams {
   const float* b3;          // [C]
   float* mean;              // [n, C]
   float* stdv;              // [n, C]
-  const uint8_t* masks;     // nullable injected keep-masks [n, T, n_sites, W]
+  const uint8_t* masks;     // nullable injected keep-masks [n, T, n_sites, mask_w]
   int n, T, W, C;
-  int n_sites, slot1, slot2;
+  int n_sites, slot1, slot2; // enabled sites in the mask tensor; slot < 0: that site has no dropout (keep everything)
+  int mask_w;               // row pitch of the injected masks (2048 when the feature site is enabled, else W)
+  int h1_per_sample;        // 1: h1 is [n * T, W] (dropout on the pooled features made hidden_0 sample dependent)
+  float inv_keep1, inv_keep2;   // 1/(1-p) behind an enabled site, 1 otherwise
   float inv_keep;
   uint32_t thresh;
   uint64_t seed, tile_base;
@@ -58,8 +61,9 @@ struct HeadSmem {
 
 __device__ __forceinline__ uint32_t keep8(const HeadParams& p, uint64_t tile, int tile_local, int t, int site, int slot,
                                           int k) {
+  if (slot < 0) return 0xFFu;                       // no dropout at this site
   if (p.masks) {
-    const uint8_t* mp = p.masks + (((int64_t)tile_local * p.T + t) * p.n_sites + slot) * p.W + k;
+    const uint8_t* mp = p.masks + (((int64_t)tile_local * p.T + t) * p.n_sites + slot) * p.mask_w + k;
     const uint2 m = *(const uint2*)mp;
     uint32_t kb = 0;
 #pragma unroll
@@ -122,7 +126,7 @@ mc_head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2 /*[W(out), W(in
       const int tl = i / (W / 8), v = i % (W / 8);
       const int tile = g * 4 + tl;
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (tile < p.n) val = __ldg((const uint4*)(p.h1 + (int64_t)tile * W + v * 8));
+      if (tile < p.n && !p.h1_per_sample) val = __ldg((const uint4*)(p.h1 + (int64_t)tile * W + v * 8));
       *(uint4*)(s_h1 + tl * kHMaxW + v * 8) = val;
     }
     __syncthreads();
@@ -187,7 +191,12 @@ mc_head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2 /*[W(out), W(in
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int k = kb * 64 + j * 8;
-              uint4 v = *(const uint4*)(s_h1 + q * kHMaxW + k);          // broadcast within the warp
+              uint4 v;
+              if (p.h1_per_sample) {                                      // one hidden_0 row per (tile, sample)
+                v = valid ? __ldg((const uint4*)(p.h1 + ((int64_t)tile_local * p.T + t) * W + k)) : make_uint4(0u, 0u, 0u, 0u);
+              } else {
+                v = *(const uint4*)(s_h1 + q * kHMaxW + k);              // broadcast within the warp
+              }
               const uint32_t kb8 = valid ? keep8(p, tile, tile_local, t, 1, p.slot1, k) : 0u;
               v.x = ((kb8 & 1u) ? (v.x & 0xFFFFu) : 0u) | ((kb8 & 2u) ? (v.x & 0xFFFF0000u) : 0u);
               v.y = ((kb8 & 4u) ? (v.y & 0xFFFFu) : 0u) | ((kb8 & 8u) ? (v.y & 0xFFFF0000u) : 0u);
@@ -214,7 +223,7 @@ mc_head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2 /*[W(out), W(in
               const uint32_t kb8 = valid ? keep8(p, tile, tile_local, t, 2, p.slot2, n0) : 0u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j8 * 8 + j]), p.inv_keep), s_b2[n0 + j]);
+                float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j8 * 8 + j]), p.inv_keep1), s_b2[n0 + j]);
                 x = __bfloat162float(__float2bfloat16_rn(fmaxf(x, 0.f)));      // h2 is a bf16 activation
                 x = (kb8 >> j) & 1u ? x : 0.f;
 #pragma unroll
@@ -239,7 +248,7 @@ mc_head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w2 /*[W(out), W(in
         float z[kMaxClasses], mx = -INFINITY, den = 0.f;
 #pragma unroll
         for (int c = 0; c < kMaxClasses; ++c)
-          if (c < C) { z[c] = __fadd_rn(__fmul_rn(logit[c], p.inv_keep), __ldg(p.b3 + c)); mx = fmaxf(mx, z[c]); }
+          if (c < C) { z[c] = __fadd_rn(__fmul_rn(logit[c], p.inv_keep2), __ldg(p.b3 + c)); mx = fmaxf(mx, z[c]); }
 #pragma unroll
         for (int c = 0; c < kMaxClasses; ++c)
           if (c < C) { z[c] = expf(z[c] - mx); den += z[c]; }

@@ -443,7 +443,8 @@ __device__ __forceinline__ uint32_t keep4(uint64_t seed, uint64_t tile, int t, i
 __global__ void __launch_bounds__(256)
 mc_expand_kernel(const bf16* __restrict__ h, bf16* __restrict__ a2, int n, int T, int width, uint64_t seed,
                  uint64_t tile_base, int site, uint32_t thresh, const uint8_t* __restrict__ masks, int n_sites,
-                 int site_slot) {
+                 int site_slot, int mask_w = 0) {
+  if (mask_w <= 0) mask_w = width;
   const int w4 = width >> 2;
   const int64_t total = (int64_t)n * T * w4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -454,7 +455,7 @@ mc_expand_kernel(const bf16* __restrict__ h, bf16* __restrict__ a2, int n, int T
     const int i = (int)(row / T);
     uint32_t kb;
     if (masks) {
-      const uint8_t* mp = masks + (((int64_t)i * T + t) * n_sites + site_slot) * width + e4 * 4;
+      const uint8_t* mp = masks + (((int64_t)i * T + t) * n_sites + site_slot) * mask_w + e4 * 4;
       kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
     } else {
       kb = keep4(seed, tile_base + (uint64_t)i, t, site, e4, thresh);

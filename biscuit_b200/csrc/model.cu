@@ -276,6 +276,10 @@ struct bq_model {
   DevBuf feat, feat_bf16;                      // [max_batch, 2048]
   DevBuf h_act[2];                             // head activations: [max_batch * T, width] bf16 (ping-pong)
   DevBuf a2;                                   // masked operand [max_batch * T, width]
+  DevBuf a0;                                   // feature-site masked operand [max_batch * T, 2048] (dropout site 0 only)
+  int sites = 6;                               // dropout-site bitmask (bq_model_config.dropout_sites)
+  int n_sites = 2, slot[3] = {-1, 0, 1};       // enabled sites and each site's slot in an injected mask tensor
+  int mask_w = 0;                              // row pitch of injected masks
   DevBuf out_mean, out_std;                    // [max_batch, classes]
   DevBuf masks_dev;
   int head_T_cap = 0;
@@ -851,9 +855,12 @@ int prepare_head(bq_model* m, int T) {
   if (rows < (size_t)m->head_batch) rows = (size_t)m->head_batch;
   if (T > m->head_T_cap) {
     BQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (auto& h : m->h_act) { h.release(); if ((rc = bq_alloc(ctx, h, rows * Wd * 2 + 1024))) return rc; }
+    const size_t hrows = (m->sites & 1) ? (size_t)(m->head_batch > B ? m->head_batch : B) * T : rows;
+    for (auto& h : m->h_act) { h.release(); if ((rc = bq_alloc(ctx, h, hrows * Wd * 2 + 1024))) return rc; }
     m->a2.release();
     if ((rc = bq_alloc(ctx, m->a2, rows * Wd * 2 + 1024))) return rc;
+    m->a0.release();
+    if ((m->sites & 1) && (rc = bq_alloc(ctx, m->a0, (size_t)B * T * kFeatures * 2 + 1024))) return rc;
     m->head_T_cap = T;
   }
   m->head_gemms.clear();
@@ -863,14 +870,16 @@ int prepare_head(bq_model* m, int T) {
     Op op;
     const PwWeights& w = *m->hidden[i];
     // layer 0: A = pooled features [B, 2048] -> h_act[0] [B, Wd]; layer i>0: A = masked operand [B*T, Wd]
-    const bf16* a = i == 0 ? (const bf16*)m->feat_bf16.p : (const bf16*)m->a2.p;
+    const bool site0 = (m->sites & 1) != 0;
+    const bf16* a = i == 0 ? (site0 ? (const bf16*)m->a0.p : (const bf16*)m->feat_bf16.p) : (const bf16*)m->a2.p;
     bf16* out = (bf16*)m->h_act[i & 1].p;
-    m->max_batch = i == 0 ? B : B * T;   // make_gemm sizes M = rows_per_tile * max_batch
-    rc = make_gemm(m, op, a, 1, w, out, 1, nullptr, i == 0 ? 1.0f : inv_keep);
+    m->max_batch = (i == 0 && !site0) ? B : B * T;   // make_gemm sizes M = rows_per_tile * max_batch
+    const float alpha = (m->sites >> i) & 1 ? inv_keep : 1.0f;        // 1/(1-p) behind an enabled site
+    rc = make_gemm(m, op, a, 1, w, out, 1, nullptr, alpha);
     m->max_batch = B;
     if (rc) return rc;
     if (i == 0) {   // layer-0 output map spans the whole head batch: micro-batches land at their row offset
-      if ((rc = make_tmap(ctx, &op.tc, out, (uint64_t)(m->head_batch > B ? m->head_batch : B), (uint64_t)w.cout,
+      if ((rc = make_tmap(ctx, &op.tc, out, (uint64_t)(m->head_batch > B ? m->head_batch : B) * (site0 ? T : 1), (uint64_t)w.cout,
                           (uint64_t)w.cout, 128, 64)))
         return rc;
     }
@@ -903,9 +912,21 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     auto& hg = m->head_gemms[i];
     GemmParams g = hg.gp;
     if (i == 0) {
-      g.M = nb;
-      g.out_row_off = h1_off;
       if (nb == 0) continue;
+      if (m->sites & 1) {
+        // dropout on the pooled features: one masked copy of the feature row per (tile, sample), so hidden_0 is per sample
+        if (!fused) return bq_fail(ctx, BQ_ERR_ARG, "dropout site 0 needs the fused head");
+        KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * kFeatures + 2.0 * nb * T * kFeatures);
+        bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (kFeatures / 4)), 256, 0, ctx->stream>>>(
+            (const bf16*)m->feat_bf16.p, (bf16*)m->a0.p, nb, T, kFeatures, seed, tile_base, 0, thresh, masks_dev, m->n_sites,
+            m->slot[0], m->mask_w);
+        BQ_LAUNCH_CHECK(ctx);
+        g.M = nb * T;
+        g.out_row_off = h1_off * T;
+      } else {
+        g.M = nb;
+        g.out_row_off = h1_off;
+      }
     } else {
       if (fused) break;
       // dropout site i: masked copy of the previous activation, one row per (tile, sample)
@@ -915,7 +936,7 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
       {
         KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * Wd + 2.0 * nb * T * Wd);
         bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (Wd / 4)), 256, 0, ctx->stream>>>(
-            src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, Hn, i - 1);
+            src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, m->n_sites, m->slot[i], m->mask_w);
       }
       BQ_LAUNCH_CHECK(ctx);
       g.M = nb * T;
@@ -937,8 +958,12 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     hp.stdv = (float*)m->out_std.p;
     hp.masks = masks_dev;
     hp.n = nb; hp.T = T; hp.W = Wd; hp.C = NC;
-    hp.n_sites = Hn; hp.slot1 = 0; hp.slot2 = 1;
+    hp.n_sites = m->n_sites; hp.slot1 = m->slot[1]; hp.slot2 = m->slot[2];
+    hp.mask_w = m->mask_w;
+    hp.h1_per_sample = (m->sites & 1) ? 1 : 0;
     hp.inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+    hp.inv_keep1 = (m->sites & 2) ? hp.inv_keep : 1.0f;
+    hp.inv_keep2 = (m->sites & 4) ? hp.inv_keep : 1.0f;
     hp.thresh = thresh;
     hp.seed = seed; hp.tile_base = tile_base;
     const int groups = (nb + 3) / 4;
@@ -949,6 +974,7 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     BQ_LAUNCH_CHECK(ctx);
     return BQ_OK;
   }
+  if (m->sites != 6) return bq_fail(ctx, BQ_ERR_ARG, "the three-kernel debug head supports the default dropout placement only");
   const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
   const int Teff = Hn == 1 ? 1 : T;
   if (Hn == 1) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers == 1 is not supported yet");
@@ -988,6 +1014,11 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->cfg = *cfg;
   m->max_batch = cfg->max_batch;
   m->px = cfg->tile_px;
+  m->sites = cfg->dropout_sites ? cfg->dropout_sites : 6;
+  if (m->sites & ~7) { delete m; return bq_fail(ctx, BQ_ERR_ARG, "dropout_sites must be a bitmask of sites 0..2"); }
+  m->n_sites = 0;
+  for (int i = 0; i < 3; ++i) m->slot[i] = (m->sites >> i) & 1 ? m->n_sites++ : -1;
+  m->mask_w = (m->sites & 1) ? kFeatures : cfg->hidden_width;
   const char* g = getenv("BQ_GEMM");
   m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
   m->gemm_direct_epi = g && strcmp(g, "direct") == 0;   // debug switch: per-thread global stores in the epilogue
@@ -1174,7 +1205,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
   BQ_CUDA(ctx, cudaSetDevice(ctx->device));
   const int B = m->max_batch, NC = m->cfg.n_classes, Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers;
   const size_t tile_bytes = (size_t)m->px * m->px * 3;
-  const size_t mask_per_tile = (size_t)T * Hn * Wd;
+  const size_t mask_per_tile = (size_t)T * m->n_sites * m->mask_w;
   const bool masks_on_dev = masks && bq_is_device_ptr(masks);
   if (masks && !masks_on_dev) {
     int rc = bq_alloc(ctx, m->masks_dev, (size_t)m->head_batch * mask_per_tile);
@@ -1236,7 +1267,10 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
     const bool last = i0 + B >= n;
     if (m->head_fused) {
       // hidden_0 now (per micro-batch); the dropout-bearing layers once enough tiles are queued to fill the SMs
-      if ((rc = run_head(m, nb, T, seed, 0, nullptr, head_count, 0))) return rc;
+      // (site 0 only: the per-sample feature masks of THIS micro-batch -- its global tile index and its slice of the masks)
+      if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0,
+                         mdev ? mdev + (size_t)head_count * mask_per_tile : nullptr, head_count, 0)))
+        return rc;
       head_count += nb;
       if (last || head_count + B > m->head_batch) {
         if ((rc = run_head(m, 0, T, seed, tile_index_base + (uint64_t)head_start, mdev, 0, head_count))) return rc;

@@ -58,7 +58,13 @@ constexpr int kNumKb = 12;                      // ceil(728 / 64); the last k-bl
 constexpr int kWStages = BQ_SM_WST;
 constexpr int kWTile = 128 * 128;               // 128 weight rows x 64 k
 constexpr int kWBytes = 3 * kWTile;             // one ring stage: the three channel tiles of a k-block
-constexpr int kInStages = 3;
+#ifndef BQ_SM_IST
+#define BQ_SM_IST 3
+#endif
+#ifndef BQ_SM_EST
+#define BQ_SM_EST 3
+#endif
+constexpr int kInStages = BQ_SM_IST;
 constexpr int kBStages = BQ_SM_BST;
 constexpr int kBBytes = kCtaPx * 128;           // 10,240 (multiple of 1024)
 constexpr int kStepPx = 40;                     // epilogue step: 40 pixels x 128 channels per CTA
@@ -67,7 +73,7 @@ constexpr int kOutStep = 8 * kOutTile;          // the eight epilogue warps
 constexpr int kOffW = 0;
 constexpr int kOffB = kOffW + kWStages * kWBytes;
 constexpr int kOffOut = kOffB + kBStages * kBBytes;
-constexpr int kEpiBufs = 3;                     // rotating epilogue buffers: residual lands / in-place epilogue / store drains
+constexpr int kEpiBufs = BQ_SM_EST;                     // rotating epilogue buffers: residual lands / in-place epilogue / store drains
 constexpr int kOffIn = kOffOut + kEpiBufs * kOutStep;
 constexpr int kOffBar = kOffIn + kInStages * kWinBytes;
 constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignment of the base
@@ -343,7 +349,9 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       mbar_expect_tx(res_full(w8, e), (uint32_t)kOutTile);
       tma_load_2d(my_out + e * kOutTile, &tmap_res, res_full(w8, e), col0, row0);
     };
-    if (has_res && elect_one()) { prefetch_res(0); prefetch_res(1); }
+    if (has_res && elect_one()) {
+      for (uint32_t i = 0; i + 1 < (uint32_t)kEpiBufs; ++i) prefetch_res(i);
+    }
     __syncwarp();
     uint32_t g = 0;                                   // running step counter of this warp
     for (int li = 0; li < my_items; ++li) {
@@ -467,7 +475,13 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           };
           auto store_step2 = [&](uint32_t gg) {
             const uint32_t e = gg % kEpiBufs;
-            if (has_res) __syncwarp();                           // every lane's ldmatrix of this buffer precedes the overwrite
+            if (has_res) {
+              __syncwarp();                                      // every lane's ldmatrix of this buffer precedes the overwrite
+            } else {
+              // buffer e was last stored from at step gg - 3: only now, two steps later, must that store have drained
+              if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kEpiBufs - 1) : "memory");
+              __syncwarp();
+            }
 #pragma unroll
             for (int b = 0; b < 5; ++b) {
               const int r = 8 * b + mrow;
@@ -483,12 +497,16 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
               for (int r2 = 0; r2 < 2; ++r2) {
                 const int row = row0 + r2 * kPitch;
                 const int y = (row / kPitch) % kPitch;
+#ifndef BQ_SM_DIAG_NOSTORE       // TIMING DIAGNOSTIC ONLY: no output traffic
                 if (y != kMap && row < p.n_rows && col0 < kC)
                   tma_store_2d(&tmap_out, my_out + e * kOutTile + r2 * kPitch * 64, col0, row);
+#endif
               }
               tma_store_commit();
-              tma_store_wait_read1();
-              if (has_res) prefetch_res(gg + 2);
+              if (has_res) {                                     // the residual of step gg + kEpiBufs - 1 lands in the buffer step gg - 1 stored from
+                tma_store_wait_read1();
+                prefetch_res(gg + kEpiBufs - 1);
+              }
             }
             __syncwarp();
           };

@@ -22,6 +22,18 @@ class ModelConfig:
     pooling: str = "avg"               # hp.py:22
     n_classes: int = 2
     uq_samples: int = 30               # Slideflow's hard-coded MC-dropout sample count
+    # where Dropout(rate) fires at inference when `uq` is on: (after the pooled 2048-d features, after hidden_0,
+    # after hidden_1).  hp.py:11-12 fix only the rate and the `uq` flag; the placement is Slideflow's and differs
+    # between its versions: (False, True, True) = after every hidden layer (default here),
+    # (True, True, True) = additionally right after `post_convolution`.
+    dropout_sites: tuple = (False, True, True)
+
+    @property
+    def dropout_site_mask(self) -> int:
+        sites = tuple(bool(x) for x in self.dropout_sites)
+        if len(sites) != self.hidden_layers + 1:
+            raise ValueError("dropout_sites needs one flag per site: pooled features + each hidden layer")
+        return sum(1 << i for i, on in enumerate(sites) if on)
 
     def replace(self, **kw) -> "ModelConfig":
         return replace(self, **kw)

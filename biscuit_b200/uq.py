@@ -69,7 +69,8 @@ class UncertaintyInterface:
         self.wsi_normalizer = None     # attribute the reference call site probes (results.py:251)
         cfg = _ffi.ModelConfig(tile_px=config.tile_px, hidden_width=config.hidden_layer_width,
                                hidden_layers=config.hidden_layers, n_classes=config.n_classes,
-                               dropout=config.dropout, max_batch=max_batch)
+                               dropout=config.dropout, max_batch=max_batch,
+                               dropout_sites=config.dropout_site_mask)
         h = C.c_void_p()
         _ffi.check(self.ctx.handle, self.lib.bq_model_create(self.ctx.handle, C.byref(cfg), C.byref(h)),
                    "bq_model_create")
@@ -129,7 +130,9 @@ class UncertaintyInterface:
         std = out_std if out_std is not None else np.empty((n, nc), np.float32)
         feats = np.empty((n, FEATURES), np.float32) if return_features else None
         if masks is not None:
-            want = (n, T, self.config.hidden_layers, self.config.hidden_layer_width)
+            sites = self.config.dropout_sites
+            width = FEATURES if sites[0] else self.config.hidden_layer_width
+            want = (n, T, sum(bool(x) for x in sites), width)
             if tuple(masks.shape) != want:
                 raise ValueError(f"masks must have shape {want}")
             if isinstance(masks, np.ndarray):

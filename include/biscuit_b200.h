@@ -137,7 +137,12 @@ typedef struct bq_model_config {
   int32_t n_classes;      /* 2                                 */
   float dropout;          /* 0.1  (hp.py:11)                   */
   int32_t max_batch;      /* tiles per backbone micro-batch    */
-  int32_t reserved[8];
+  /* MC-dropout placement, bit i = a Dropout(rate) active at inference after site i:
+   *   bit 0: the pooled 2048-d features (Slideflow's `post_convolution`), bit 1: hidden_0, bit 2: hidden_1.
+   * 0 selects the default 0b110 (after each hidden layer).  Which placement a saved model has depends on the
+   * Slideflow version that built it (hp.py:11-12 only fix the rate and `uq`); INTEGRATION.md lists both. */
+  int32_t dropout_sites;
+  int32_t reserved[7];
 } bq_model_config;
 
 typedef struct bq_named_tensor {
@@ -159,6 +164,8 @@ int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n
  *   masks   nullable injected keep-masks uint8 [n, T, hidden_layers, hidden_width] (1 = keep)
  *   mean, std   float32 [n, n_classes]   (y_pred / uncertainty columns of utils.py:19-28 = class 1)
  *   features    nullable float32 [n, 2048] post-pooling features                                   */
+/* injected keep-masks (parity tests): uint8 [n, T, n_enabled_sites, mask_width], enabled sites in ascending order,
+ * mask_width = 2048 when site 0 is enabled, else hidden_width */
 int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint64_t seed,
                   uint64_t tile_index_base, const uint8_t* masks, float* mean, float* std,
                   float* features);

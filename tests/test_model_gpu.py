@@ -407,3 +407,50 @@ def test_fused_middle_flow_agrees_with_separate_kernels():
     assert d[4 * n:4 * n + n * 2048].max() <= 2e-2 * np.abs(f).max()
     b12 = a[4 * n + n * 2048:]
     assert d[4 * n + n * 2048:].max() <= 3e-2 * np.abs(b12).max()
+
+
+@pytest.mark.parametrize("sites", [(True, True, True), (True, False, True), (False, False, True)])
+def test_dropout_site_placements_vs_oracle(weights, tiles, oracle_bf16, sites):
+    """MC-dropout placement is a model property that depends on the Slideflow version:
+    `ModelConfig.dropout_sites` = (after the pooled 2048-d features, after hidden_0, after hidden_1).  With site 0 on,
+    hidden_0 is evaluated per (tile, sample) on the masked features.  Injected masks vs the oracle's head, and the
+    kernels' own Philox stream == the oracle's masks, for every placement."""
+    from biscuit_b200.hp import nature2022
+    from biscuit_b200.uq import UncertaintyInterface
+    cfg = nature2022.replace(dropout_sites=sites)
+    it = UncertaintyInterface(weights, config=cfg, max_batch=4)
+    try:
+        enabled = [i for i, on in enumerate(sites) if on]
+        width = 2048 if sites[0] else 1024
+        masks = X.keep_masks(N_TILES, T, width, 0.1, SEED, sites=enabled)
+        mean, std = it.predict(tiles, T=T, masks=masks)
+        o = X.XceptionUQOracle(weights, emulate_bf16=True, dropout_sites=sites)
+        m_ref, s_ref = o.predict_uq(tiles, T=T, masks=masks)
+        print(sites, "d_mean", np.abs(mean - m_ref).max(), "d_std", np.abs(std - s_ref).max())
+        assert np.abs(mean - m_ref).max() <= 4e-3 and np.abs(std - s_ref).max() <= 4e-3
+        own = it.predict(tiles, T=T, seed=SEED)
+        assert np.array_equal(own[0], mean) and np.array_equal(own[1], std)      # Philox stream == injected masks
+        # a different placement gives a different answer (the option is not a no-op)
+        base, _, _ = oracle_bf16
+        m_def, s_def = base.predict_uq(tiles, T=T, seed=SEED)
+        assert np.abs(s_ref - s_def).max() > 1e-4
+        # sample counts beyond one 32-slot chunk, partial micro-batch
+        m70 = X.keep_masks(N_TILES, 70, width, 0.1, 5, sites=enabled)
+        a = it.predict(tiles, T=70, masks=m70)
+        b = o.predict_uq(tiles, T=70, masks=m70)
+        assert np.abs(a[0] - b[0]).max() <= 4e-3 and np.abs(a[1] - b[1]).max() <= 4e-3
+    finally:
+        it.close()
+
+
+def test_dropout_sites_config_errors(weights):
+    from biscuit_b200.hp import nature2022
+    from biscuit_b200.uq import UncertaintyInterface
+    with pytest.raises(ValueError):
+        UncertaintyInterface(weights, config=nature2022.replace(dropout_sites=(True, True)), max_batch=2)
+    it = UncertaintyInterface(weights, config=nature2022.replace(dropout_sites=(True, True, True)), max_batch=2)
+    try:
+        with pytest.raises(ValueError):                           # masks of the default placement's shape are rejected
+            it.predict(np.zeros((1, 299, 299, 3), np.uint8), T=2, masks=np.ones((1, 2, 2, 1024), np.uint8))
+    finally:
+        it.close()
