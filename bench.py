@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target size of the CPU-baseline sample")
+    ap.add_argument("--workload", default="wsi", choices=["wsi", "cohort"],
+                    help="wsi: BASELINE configs[1] (headline, weak scaling); cohort: configs[2], --slides x --tiles sharded by "
+                         "whole slides over the ranks (strong scaling), slide-level thresholding through apply_sharded")
     return ap.parse_args()
 
 
@@ -329,6 +332,113 @@ def run_native_arm(args, rank, world, local_rank):
     return out
 
 
+def run_cohort_arm(args, rank, world, local_rank):
+    """BASELINE configs[2]: a cohort of `--slides` slides x `--tiles` tiles sharded over the ranks by WHOLE slides
+    (dist.shard_bounds), MC-dropout inference on each rank's slides, then ONE exchange of per-slide aggregates and the
+    replicated slide-level thresholding (threshold.apply_sharded).  Strong scaling: the cohort is fixed, ranks split it.
+    Tiles are synthetic and generated on the device: a pool of distinct slides is cycled (2 M real tiles would be 536 GB);
+    every slide still draws its own dropout masks (Philox counters carry the global tile index)."""
+    import pandas as pd
+    import torch
+    import torch.distributed as dist
+    from biscuit_b200 import _ffi, threshold
+    from biscuit_b200 import dist as bdist
+    from biscuit_b200.uq import UncertaintyInterface
+    from biscuit_b200.weights import random_init
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    ctx = _ffi.default_context(local_rank)
+    iface = UncertaintyInterface(random_init(seed=1), max_batch=args.max_batch, ctx=ctx)
+    S, Tn = args.slides, args.tiles
+    lo, hi = bdist.shard_bounds([Tn] * S, world)[rank]
+    pool_n = min(8, max(1, hi - lo))
+    pool = [synth_tiles_device(Tn, device, seed=5000 + j) for j in range(pool_n)]
+    torch.cuda.synchronize()
+    names = np.array([f"slide{j:05d}" for j in range(S)], dtype=object)
+    labels = (np.random.default_rng(7).random(S) < 0.5).astype(np.int64)
+    n_local = (hi - lo) * Tn
+    mean = np.empty((n_local, 2), np.float32)
+    std = np.empty((n_local, 2), np.float32)
+    thresholds = dict(tile_uq=0.06, slide_uq=0.055, tile_pred=0.5, slide_pred=0.5)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def one_step(step):
+        for k, sl in enumerate(range(lo, hi)):
+            iface.predict(pool[k % pool_n], T=args.T, seed=step, tile_index_base=sl * Tn,
+                          out_mean=mean[k * Tn:(k + 1) * Tn], out_std=std[k * Tn:(k + 1) * Tn])
+        df = pd.DataFrame({"slide": np.repeat(names[lo:hi], Tn), "y_true": np.repeat(labels[lo:hi], Tn),
+                           "y_pred": mean[:, 1], "uncertainty": std[:, 1]})
+        if world > 1:
+            return threshold.apply_sharded(df, **thresholds), df
+        return threshold.apply(df, **thresholds), df
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    for s_ in range(args.warmup):
+        one_step(s_)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launches
+    w0 = time.perf_counter()
+    with torch.cuda.stream(ext_stream):
+        e0.record()
+    for s_ in range(args.steps):
+        (res, s_df), df_local = one_step(args.warmup + s_)
+    with torch.cuda.stream(ext_stream):
+        e1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0]), float(t[1]) / 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    # sharded decisions == single-process apply on the concatenated table (bit for bit), checked on rank 0
+    same = None
+    if world > 1:
+        meta = bdist.all_gather_meta([len(df_local)])
+        parts = bdist.all_gather_bytes(bdist.pack_tiles(df_local["y_pred"].to_numpy(), df_local["uncertainty"].to_numpy(),
+                                                        df_local["y_true"].to_numpy().astype(np.uint8)),
+                                       [int(m[0]) * 9 for m in meta], device=f"cuda:{local_rank}")
+        if rank == 0:
+            cols = [bdist.unpack_tiles(p_, int(m[0]), np.float32) for m, p_ in zip(meta, parts)]
+            full = pd.DataFrame({"slide": np.repeat(names, Tn), "y_true": np.concatenate([c[2] for c in cols]).astype(np.int64),
+                                 "y_pred": np.concatenate([c[0] for c in cols]), "uncertainty": np.concatenate([c[1] for c in cols])})
+            r1, s1 = threshold.apply(full, **thresholds)
+            same = bool(all((r1[k] == res[k]) or (r1[k] != r1[k] and res[k] != res[k]) for k in r1) and
+                        ((s1 is None and s_df is None) or (s1 is not None and s_df is not None and s1.equals(s_df))))
+    if rank != 0:
+        return None
+    total_tiles = S * Tn * args.steps
+    value = total_tiles / (ms / 1e3)
+    return {
+        "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"configs[2]: cohort of {S} synthetic slides x {Tn} tiles, T={args.T}, tiles sharded by whole slides "
+                               f"over {world} GPU(s), per-slide aggregates all-gathered, threshold.apply_sharded",
+                   "slides": S, "tiles_per_slide": Tn, "T": args.T, "max_batch": args.max_batch,
+                   "cache": f"a pool of {pool_n} distinct slides ({pool_n * Tn * TILE_BYTES / 1e9:.2f} GB) cycled per rank >> 126 MB L2"},
+        "slides_per_sec": value / Tn, "wall_ms_per_step": wall * 1e3 / args.steps,
+        "sharded_equals_single_process_apply": same, "slides_included": None if s_df is None else int(len(s_df)),
+        "apply_results": {k: (None if v is None or v != v else float(v)) for k, v in res.items()},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": None, "roofline": None,
+        "cpu_baseline": {"value": None, "unit": "tiles/s", "cores": 0, "kind": "port",
+                         "sample": "not measured in the cohort workload (see the headline wsi line)"},
+    }
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -344,6 +454,14 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    if args.workload == "cohort":
+        out = run_cohort_arm(args, rank, world, local_rank)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps(out))
+        return
     out = run_native_arm(args, rank, world, local_rank)
     if rank == 0 and world > 1:
         # the CPU baseline is a rank-0, N = 1 measurement (torchrun pins OMP_NUM_THREADS=1 and the other ranks would

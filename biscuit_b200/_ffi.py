@@ -50,6 +50,11 @@ SIGNATURES = {
     "bq_launch_count": (C.c_int64, [C.c_void_p]),
     "bq_sync": (C.c_int, [C.c_void_p]),
     "bq_stream": (C.c_void_p, [C.c_void_p]),
+    "bq_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "bq_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "bq_comm_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "bq_comm_destroy": (None, [C.c_void_p]),
+    "bq_allgather_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bq_table_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, c_void_pp]),
     "bq_table_destroy": (None, [C.c_void_p]),

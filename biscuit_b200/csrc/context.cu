@@ -59,6 +59,7 @@ int bq_create(int device, bq_ctx** out) {
 
 void bq_destroy(bq_ctx* ctx) {
   if (!ctx) return;
+  bq_comm_destroy(ctx);                     // no-op without a communicator
   cudaSetDevice(ctx->device);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);

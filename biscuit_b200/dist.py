@@ -79,7 +79,49 @@ def all_gather_groups(msg: np.ndarray, group=None, device=None):
 # ----------------------------------------------------------------------------------------------------------------
 # byte-level collectives (tensor all-gathers only: no pickled objects, so the exchange stays on NCCL / NVLink)
 # ----------------------------------------------------------------------------------------------------------------
+class NativeComm:
+    """NCCL communicator owned by the C library (`bq_comm_init`, include/biscuit_b200.h): pass it as `group=` to
+    `threshold.apply_sharded / detect_sharded` and the exchange step runs through the C ABI (`bq_allgather_bytes`) on
+    the context's stream instead of torch.distributed -- the path a non-Python host drives.
+
+    Rank 0 obtains `NativeComm.unique_id()` and ships the 128 bytes to the other ranks by any host-side channel."""
+
+    def __init__(self, ctx, rank: int, world: int, unique_id: bytes):
+        from . import _ffi
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of bq_comm_unique_id")
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        _ffi.check(ctx.handle, ctx.lib.bq_comm_init(ctx.handle, self.rank, self.world, _ffi.ptr(buf)), "bq_comm_init")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        from . import _ffi
+        lib = _ffi.load_library()
+        buf = np.zeros(128, np.uint8)
+        rc = lib.bq_comm_unique_id(_ffi.ptr(buf))
+        if rc != 0:
+            raise _ffi.NativeLibraryError(f"bq_comm_unique_id failed (rc={rc}): NCCL unavailable")
+        return buf.tobytes()
+
+    def all_gather_fixed(self, buf: np.ndarray) -> np.ndarray:
+        """uint8 [n] from every rank -> uint8 [world, n] in rank order"""
+        from . import _ffi
+        buf = np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+        out = np.empty((self.world, buf.shape[0]), np.uint8)
+        _ffi.check(self.ctx.handle, self.ctx.lib.bq_allgather_bytes(self.ctx.handle, _ffi.ptr(buf), buf.shape[0],
+                                                                    _ffi.ptr(out)), "bq_allgather_bytes")
+        return out
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self.ctx.lib.bq_comm_destroy(self.ctx.handle)
+            self.ctx = None
+
+
 def _dist_state(group=None):
+    if isinstance(group, NativeComm):
+        return group, group.world, group.rank
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
         return None, 1, 0
@@ -98,6 +140,8 @@ def all_gather_meta(values, group=None, device=None):
     v = np.asarray(values, dtype=np.int64).reshape(1, -1)
     if world == 1:
         return v
+    if isinstance(group, NativeComm):
+        return group.all_gather_fixed(v.view(np.uint8).reshape(-1)).copy().view(np.int64).reshape(world, v.shape[1])
     dev = _collective_device(dist, group, device)
     t = torch.from_numpy(v[0].copy()).to(dev)
     out = torch.empty(world * v.shape[1], dtype=torch.int64, device=dev)     # flat: gloo requires world * numel
@@ -115,6 +159,11 @@ def all_gather_bytes(buf, sizes, group=None, device=None):
         return [buf]
     sizes = [int(x) for x in sizes]
     pad = max(max(sizes), 1)
+    if isinstance(group, NativeComm):
+        send = np.zeros(pad, np.uint8)
+        send[: buf.shape[0]] = buf
+        host = group.all_gather_fixed(send)
+        return [host[r, : sizes[r]] for r in range(world)]
     dev = _collective_device(dist, group, device)
     t = torch.zeros(pad, dtype=torch.uint8, device=dev)
     if buf.shape[0]:

@@ -193,6 +193,27 @@ int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flo
                             double bytes[BQ_PROFILE_KINDS], int64_t launches[BQ_PROFILE_KINDS]);
 
 /* ------------------------------------------------------------------------------------------------
+ * multi-GPU exchange (one process -- or host thread -- per GPU)
+ *   The reference is single-process (no collective anywhere under /root/reference).  Here tiles shard over GPUs by whole
+ *   slides, so the per-slide reduction (threshold.py:191-192) stays local and bit-exact; what crosses GPUs is
+ *     - the per-slide aggregates {code, count, first_row, y_pred, uncertainty, y_true_mean} (6 x float64 per slide)
+ *       before the slide-level stage of `apply` (threshold.py:304-348) / `detect` (threshold.py:433-468), and
+ *     - for `detect` only, the per-tile (y_pred, uncertainty, y_true) triples feeding the cohort-wide tile ROCs
+ *       (threshold.py:145-152, 419-424).
+ *   Both are all-gathers of one byte block per rank.
+ * ---------------------------------------------------------------------------------------------- */
+#define BQ_COMM_ID_BYTES 128
+/* rank 0 creates the NCCL unique id and hands it to the other ranks by any host-side means (file, MPI, pipe ...) */
+int bq_comm_unique_id(uint8_t id[BQ_COMM_ID_BYTES]);
+/* collective over all ranks: attaches an NCCL communicator (NVLink / NVSwitch) to this context */
+int bq_comm_init(bq_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[BQ_COMM_ID_BYTES]);
+int bq_comm_size(bq_ctx* ctx, int32_t* rank, int32_t* world);   /* (0, 1) without a communicator */
+void bq_comm_destroy(bq_ctx* ctx);
+/* every rank sends `nbytes` (the same on all ranks; callers pad to the largest block) and receives world * nbytes in
+ * rank order.  Host or device pointers; runs on the ctx stream and returns when `recv` is complete. */
+int bq_allgather_bytes(bq_ctx* ctx, const void* send, int64_t nbytes, void* recv);
+
+/* ------------------------------------------------------------------------------------------------
  * stain normalisation in front of per-image standardisation
  *   replaces `interface.wsi_normalizer.rgb_to_rgb(image)` (results.py:251-254) for hp.normalizer ==
  *   'reinhard_fast' (biscuit/hp.py:19); arithmetic restated from slideflow/norm/tensorflow/reinhard.py

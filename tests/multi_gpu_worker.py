@@ -37,6 +37,61 @@ def main():
     assert_same_results(ref_res, res, f"rank {rank}")
     assert_same_df(ref_s, s_df, f"rank {rank}")
 
+    # (1b) cohort-wide detection on the sharded table: tile ROCs over ALL tiles (triples all-gathered), slide level replicated
+    ref_th, ref_auc = O.detect(df.copy())
+    th2, auc2 = threshold.detect_sharded(df.iloc[r0:r1].reset_index(drop=True))
+    assert_same_results(ref_th, th2, f"detect rank {rank}")
+    assert (ref_auc == auc2) or (ref_auc != ref_auc and auc2 != auc2), (ref_auc, auc2)
+    # ... and with numeric tile thresholds / no tile-UQ filter (no triple exchange needed)
+    for kw in (dict(tile_uq=0.05, tile_pred=0.5), dict(tile_uq=None, slide_uq=None, tile_pred=np.float64(0.4), slide_pred=0.5)):
+        a, _ = O.detect(df.copy(), **kw)
+        b, _ = threshold.detect_sharded(df.iloc[r0:r1].reset_index(drop=True), **kw)
+        assert_same_results(a, b, f"detect {kw} rank {rank}")
+    # from_cv over sharded folds
+    folds = synth.cv_tables(k=3, n_slides=24, tiles_per_slide=70, seed0=300)
+    shards = []
+    for f in folds:
+        c = f.groupby("slide", sort=False).size().to_numpy()
+        a, b = bdist.shard_bounds(c, world)[rank]
+        shards.append(f.iloc[int(c[:a].sum()):int(c[:b].sum())].reset_index(drop=True))
+    assert_same_results(O.from_cv([f.copy() for f in folds]), threshold.from_cv_sharded(shards), f"from_cv rank {rank}")
+
+    # (1c) the same exchange through the C ABI communicator (bq_comm_init / bq_allgather_bytes) instead of torch.distributed
+    from biscuit_b200 import _ffi
+    ctx = _ffi.default_context(local)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(bdist.NativeComm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    comm = bdist.NativeComm(ctx, rank, world, bytes(idt.cpu().numpy().tobytes()))
+    res3, s3 = threshold.apply_sharded(df.iloc[r0:r1].reset_index(drop=True), group=comm, **th)
+    assert_same_results(ref_res, res3, f"native comm rank {rank}")
+    assert_same_df(ref_s, s3, f"native comm rank {rank}")
+    th3, _ = threshold.detect_sharded(df.iloc[r0:r1].reset_index(drop=True), group=comm)
+    assert_same_results(ref_th, th3, f"native comm detect rank {rank}")
+    comm.close()
+
+    # (1d) an EMPTY shard (more ranks than slides) and a validation error on ONE rank: nobody blocks, everyone agrees
+    one = synth.tile_table(n_slides=1, tiles_per_slide=50, seed=7)
+    mine = one if rank == 0 else one.iloc[0:0]
+    r_one, s_one = threshold.apply_sharded(mine.reset_index(drop=True), tile_uq=0.05, slide_uq=0.03)
+    a_one, b_one = O.apply(one.copy(), tile_uq=0.05, slide_uq=0.03)
+    assert_same_results(a_one, r_one, f"empty shard rank {rank}")
+    bad = local_df.copy()
+    if rank == world - 1:
+        bad.loc[bad.index[3], "y_pred"] = np.nan
+    from biscuit_b200.errors import PredsContainNaNError
+    try:
+        threshold.apply_sharded(bad, **th)
+        raise AssertionError("expected PredsContainNaNError on every rank")
+    except PredsContainNaNError:
+        pass
+    try:
+        threshold.apply_sharded(local_df.copy(), tile_uq=0.05, slide_uq=0.03, tile_pred="detect")
+        raise AssertionError("expected ValueError for a per-shard 'detect'")
+    except ValueError:
+        pass
+
     # (2) inference: shards draw disjoint Philox streams (tile_index_base) == one process over all tiles
     tiles = synth.tiles_u8(8, seed=3, n_slides=4)
     iface = UncertaintyInterface(random_init(seed=1), max_batch=4, device=local)

@@ -204,3 +204,43 @@ def test_apply_sharded_single_rank_equals_apply(T):
         assert_same_results(x[0], y[0])
         assert_same_df(x[1], y[1])
         assert_same_df(a, b)
+
+
+def test_detect_sharded_single_rank_equals_detect(T):
+    """world == 1: the sharded entry points degenerate to the single-process functions (collectives pass through), bit-exact
+    vs the oracle incl. the mutation of the table; heavy-ties and f64 tables; from_cv_sharded over folds."""
+    for kw in (dict(n_slides=30, tiles_per_slide=80, seed=51), dict(n_slides=18, tiles_per_slide=50, seed=52, ties=50),
+               dict(n_slides=22, tiles_per_slide=40, seed=53, dtype=np.float64, ragged=True)):
+        df = synth.tile_table(**kw)
+        for dkw in ({}, dict(tile_uq=0.05), dict(tile_uq=None, slide_uq=None), dict(tile_pred=0.5, slide_pred=np.float64(0.45))):
+            a, b = df.copy(), df.copy()
+            x, y = O.detect(a, **dkw), T.detect_sharded(b, **dkw)
+            assert_same_results(x[0], y[0], f"{kw} {dkw}")
+            assert same_scalar(x[1], y[1]), (x[1], y[1])
+            assert_same_df(a, b)
+    folds = synth.cv_tables(k=4, n_slides=25, tiles_per_slide=60, seed0=70)
+    assert_same_results(O.from_cv([f.copy() for f in folds]), T.from_cv_sharded([f.copy() for f in folds]))
+    # NaN predictions: the reference logs and returns all-None (threshold.py:403-405)
+    bad = synth.tile_table(n_slides=6, tiles_per_slide=20, seed=54)
+    bad.loc[5, "y_pred"] = np.nan
+    th, auc = T.detect_sharded(bad)
+    assert all(v is None for v in th.values()) and auc is None
+    with pytest.raises(ValueError):
+        T.apply_sharded(synth.tile_table(n_slides=4, tiles_per_slide=10, seed=1), 0.05, 0.03, tile_pred="detect")
+
+
+def test_native_comm_world1_passthrough(T):
+    """bq_comm_* / bq_allgather_bytes without a communicator behave as a world of one (the 2-rank NCCL run lives in
+    tests/multi_gpu_worker.py)."""
+    import ctypes as C
+    from biscuit_b200 import _ffi
+    ctx = _ffi.default_context()
+    r, w = C.c_int32(-1), C.c_int32(-1)
+    assert ctx.lib.bq_comm_size(ctx.handle, C.byref(r), C.byref(w)) == 0 and (r.value, w.value) == (0, 1)
+    src = np.arange(37, dtype=np.uint8)
+    dst = np.zeros(37, np.uint8)
+    assert ctx.lib.bq_allgather_bytes(ctx.handle, _ffi.ptr(src), 37, _ffi.ptr(dst)) == 0
+    assert np.array_equal(src, dst)
+    uid = _ffi.load_library().bq_comm_unique_id
+    buf = np.zeros(128, np.uint8)
+    assert uid(_ffi.ptr(buf)) == 0 and buf.any()
