@@ -50,6 +50,9 @@ SIGNATURES = {
     "bq_launch_count": (C.c_int64, [C.c_void_p]),
     "bq_sync": (C.c_int, [C.c_void_p]),
     "bq_stream": (C.c_void_p, [C.c_void_p]),
+    "bq_heatmap_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
+    "bq_heatmap_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "bq_comm_unique_id": (C.c_int, [C.c_void_p]),
     "bq_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bq_comm_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -76,6 +79,8 @@ SIGNATURES = {
     "bq_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(NamedTensor), C.c_int32]),
     "bq_predict_uq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bq_predict_uq_standardized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
+                                             C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bq_model_debug_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_void_p,
                                        C.c_int64, C.POINTER(C.c_int64)]),
     "bq_stain_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

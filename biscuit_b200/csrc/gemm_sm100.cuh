@@ -12,10 +12,11 @@
 //     serves all nine taps; rows whose (y, x) fall outside the valid output window are dropped in the epilogue;
 //   * dense layers: scale = 1 (or 1/(1-p) after a dropout site), shift = bias.
 //
-// Structure (one CTA per SM, persistent over output tiles, warp specialised):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d into a STAGES-deep smem ring (128B / 64B swizzle)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x 256 cols)
-//   warps 2-5: epilogue      -- tcgen05.ld 32x32b.x32 -> registers -> scale/shift/residual/ReLU -> bf16 -> 16 B stores
+// Structure (one CTA per SM, CTA pairs on a TPC, persistent over output tiles, warp specialised):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d into a STAGES-deep smem ring (128B swizzle)
+//   warp 1   : TMEM allocator + tcgen05.mma issue (one elected lane of the converged warp), accumulators double-buffered
+//              in TMEM (2 x 256 columns)
+//   warps 2-9: epilogue      -- tcgen05.ld 32x32b.x32 -> registers -> scale/shift/residual/ReLU -> bf16 -> smem -> TMA store
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 #pragma once
 
@@ -206,314 +207,6 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" 
 constexpr int kEpiCols = 64;                       // epilogue chunk: 128 rows x 64 bf16 columns = 16 KB
 constexpr int kEpiBytes = kBM * kEpiCols * 2;
 
-// TMA_EPI = true : output (and residual) tiles move through shared memory with TMA (coalesced 128-byte rows,
-//                  hardware clipping of the M / N tails); 3 operand stages.
-// TMA_EPI = false: each epilogue thread stores its own row directly (used by the implicit 3x3 convolution, whose
-//                  rows are compacted on the way out, 128 contiguous bytes per thread).
-template <int BLOCK_K, bool TMA_EPI>
-struct SmemPlan {
-  static constexpr int kStages = TMA_EPI ? 3 : (BLOCK_K == 64 ? 4 : 6);
-  static constexpr int kABytes = kBM * BLOCK_K * 2;
-  static constexpr int kBBytes = kBNMax * BLOCK_K * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutOffset = kStages * kStageBytes;             // 2 x out staging, 2 x residual staging
-  static constexpr int kResOffset = kOutOffset + (TMA_EPI ? 2 * kEpiBytes : 0);
-  static constexpr int kBarOffset = kResOffset + (TMA_EPI ? 2 * kEpiBytes : 0);
-  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + tmem slot, + slack for 1024 B alignment
-};
-
-template <int BLOCK_K, bool TMA_EPI>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                    const GemmParams p) {
-  using Plan = SmemPlan<BLOCK_K, TMA_EPI>;
-  constexpr int STAGES = Plan::kStages;
-  constexpr int SWZ = BLOCK_K * 2;     // bytes per smem row == swizzle span
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));      // generic pointer to the aligned base
-  const uint32_t bar_base = smem_base + Plan::kBarOffset;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kAccStages + a); };
-  auto res_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 * kAccStages + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * kAccStages + 2);
-  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem_gen + Plan::kBarOffset + 8 * (2 * STAGES + 2 * kAccStages + 2));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kBM - 1) / kBM;
-  const int n_tiles = (p.N + p.bn_box - 1) / p.bn_box;
-  const int total_tiles = m_tiles * n_tiles;
-  const int num_kb = p.conv_mode ? 9 : (p.K + BLOCK_K - 1) / BLOCK_K;
-  const uint32_t stage_tx = Plan::kABytes + (uint32_t)p.bn_box * BLOCK_K * 2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    if (TMA_EPI) { tma_prefetch_desc(&tmap_out); if (p.residual) tma_prefetch_desc(&tmap_res); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < kAccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-    mbar_init(res_bar(0), 1); mbar_init(res_bar(1), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), stage_tx);
-          const uint32_t a_dst = smem_base + s * Plan::kStageBytes, b_dst = a_dst + Plan::kABytes;
-          if (p.conv_mode) {
-            tma_load_2d(a_dst, &tmap_a, full_bar(s), 0, m0 + (kb / 3) * p.in_w + (kb % 3));
-          } else {
-            tma_load_2d(a_dst, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
-          }
-          tma_load_2d(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      int as = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * p.bn_box;
-        int n_cols = p.N - n0;
-        if (n_cols > p.bn_box) n_cols = p.bn_box;
-        n_cols = (n_cols + 15) & ~15;
-        const uint32_t idesc = make_idesc(kBM, n_cols);
-        mbar_wait(tempty_bar(as), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t a_src = smem_base + s * Plan::kStageBytes, b_src = a_src + Plan::kABytes;
-          int ksteps = BLOCK_K / 16;
-          if (!p.conv_mode && kb == num_kb - 1) {
-            const int tail = p.K - kb * BLOCK_K;     // TMA zero-fills columns >= K
-            ksteps = (tail + 15) / 16;
-          }
-          const uint64_t da = make_smem_desc<SWZ>(a_src), db = make_smem_desc<SWZ>(b_src);
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(s));                       // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-        if (++as == kAccStages) { as = 0; aph ^= 1u; }
-      }
-    }
-  } else {
-    // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    int as = 0; uint32_t aph = 0;
-    if constexpr (TMA_EPI) {
-      const bool leader = (warp == 2 && lane == 0);
-      const bool has_res = p.residual != nullptr;
-      uint32_t cc = 0;                                   // running chunk counter: buffer = cc & 1
-      if (leader && has_res && (int)blockIdx.x < total_tiles) {
-        const int t0 = blockIdx.x;
-        mbar_expect_tx(res_bar(0), kEpiBytes);
-        tma_load_2d(smem_base + Plan::kResOffset, &tmap_res, res_bar(0), (t0 % n_tiles) * p.bn_box, (t0 / n_tiles) * kBM);
-      }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
-        int n_cols = p.N - n0;
-        if (n_cols > p.bn_box) n_cols = p.bn_box;
-        mbar_wait(tfull_bar(as), aph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
-        for (int c = 0; c < n_cols; c += kEpiCols, ++cc) {
-          const uint32_t buf = cc & 1u;
-          uint8_t* out_st = smem_gen + Plan::kOutOffset + buf * kEpiBytes;
-          const uint8_t* res_st = smem_gen + Plan::kResOffset + buf * kEpiBytes;
-          uint32_t v[64];
-          {
-            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-            tmem_ld_32x32b_x32(t_row + (uint32_t)c, v0);
-            tmem_ld_32x32b_x32(t_row + (uint32_t)c + 32u, v1);
-            tmem_ld_wait();
-          }
-          if (has_res) mbar_wait(res_bar(buf), (cc >> 1) & 1u);
-          const int n = n0 + c;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-            if (n + g * 8 < p.N) {
-              if (p.scale) {
-                const float4 s0 = __ldg((const float4*)(p.scale + n + g * 8));
-                const float4 s1 = __ldg((const float4*)(p.scale + n + g * 8 + 4));
-                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], sc[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], p.alpha);
-              }
-              if (p.shift) {
-                const float4 h0 = __ldg((const float4*)(p.shift + n + g * 8));
-                const float4 h1 = __ldg((const float4*)(p.shift + n + g * 8 + 4));
-                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], sh[j]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = 0.f;
-            }
-            const uint32_t sw_off = (uint32_t)row_in_tile * 128u + (uint32_t)((g ^ (row_in_tile & 7)) << 4);
-            if (has_res) {
-              const uint4 r = *(const uint4*)(res_st + sw_off);
-              const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 rf = __bfloat1622float2(rb[j]);
-                f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            uint4 o;
-            __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            *(uint4*)(out_st + sw_off) = o;
-          }
-          fence_async_smem();                       // generic-proxy smem writes -> visible to the TMA engine
-          if (leader) tma_store_wait_read0();       // the previous chunk's store has finished reading its buffer
-          epi_barrier();
-          if (leader) {
-            tma_store_2d(&tmap_out, smem_base + Plan::kOutOffset + buf * kEpiBytes, n, m0 + p.out_row_off);
-            tma_store_commit();
-            if (has_res) {
-              // prefetch the residual chunk of the NEXT epilogue step into the other buffer (its last readers
-              // finished before the barrier above)
-              int nt = tile, nc = c + kEpiCols;
-              if (nc >= n_cols) { nt = tile + gridDim.x; nc = 0; }
-              if (nt < total_tiles) {
-                mbar_expect_tx(res_bar(buf ^ 1u), kEpiBytes);
-                tma_load_2d(smem_base + Plan::kResOffset + (buf ^ 1u) * kEpiBytes, &tmap_res, res_bar(buf ^ 1u),
-                            (nt % n_tiles) * p.bn_box + nc, (nt / n_tiles) * kBM);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
-        if (++as == kAccStages) { as = 0; aph ^= 1u; }
-      }
-      if (leader) tma_store_wait_all();
-    } else {
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * p.bn_box;
-        int n_cols = p.N - n0;
-        if (n_cols > p.bn_box) n_cols = p.bn_box;
-        const int m = m0 + row_in_tile;
-        // output row (conv mode drops rows outside the valid window and compacts the rest)
-        long long orow = m;
-        bool row_ok = m < p.M;
-        if (p.conv_mode && row_ok) {
-          const int img = m / p.in_hw, rem = m - img * p.in_hw;
-          const int y = rem / p.in_w, x = rem - y * p.in_w;
-          row_ok = (y < p.out_h) && (x < p.out_w);
-          orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
-        }
-        mbar_wait(tfull_bar(as), aph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBNMax);
-        for (int c = 0; c < n_cols; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int n = n0 + c;
-            __nv_bfloat16* optr = p.out + (orow + p.out_row_off) * p.ldc + n;
-            const __nv_bfloat16* rptr = p.residual ? p.residual + orow * p.ldr + n : nullptr;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (n + g * 8 < p.N) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                // separately rounded multiply and add (no FMA contraction): same rounding sequence as the
-                // oracle's `acc * scale + shift`
-                if (p.scale) {
-                  const float4 s0 = __ldg((const float4*)(p.scale + n + g * 8));
-                  const float4 s1 = __ldg((const float4*)(p.scale + n + g * 8 + 4));
-                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], sc[j]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], p.alpha);
-                }
-                if (p.shift) {
-                  const float4 h0 = __ldg((const float4*)(p.shift + n + g * 8));
-                  const float4 h1 = __ldg((const float4*)(p.shift + n + g * 8 + 4));
-                  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], sh[j]);
-                }
-                if (rptr) {
-                  const uint4 r = *(const uint4*)(rptr + g * 8);
-                  const __nv_bfloat162* rb = (const __nv_bfloat162*)&r;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 rf = __bfloat1622float2(rb[j]);
-                    f[2 * j] = __fadd_rn(f[2 * j], rf.x); f[2 * j + 1] = __fadd_rn(f[2 * j + 1], rf.y);
-                  }
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-                }
-                uint4 o;
-                __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                *(uint4*)(optr + g * 8) = o;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
-        if (++as == kAccStages) { as = 0; aph ^= 1u; }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // =====================================================================================================
 // 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x N tile with ONE tcgen05.mma stream.
 // Each CTA stages its own 128 rows of A and HALF of the B tile (N/2 rows), so operand traffic from L2 per
@@ -531,13 +224,11 @@ constexpr int k2EpiWarps = 8;                        // two warps per TMEM lane 
 constexpr int k2Threads = 64 + 32 * k2EpiWarps;      // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
 constexpr int k2MaxN = 2048;
 constexpr int k2ResBufs = 3;                         // residual chunks in flight (prefetch distance 2)                         // per-channel scale/shift staged in smem for the whole N
-constexpr int k2WideN = 384;                         // WIDE: one 256 x 384 accumulator per CTA pair (256 + 128 columns, two MMAs per k-step)
-template <int STAGES, bool WIDE = false>
+template <int STAGES>
 struct SmemPlan2 {
   static constexpr int kABytes = kBM * 64 * 2;                 // 16 KB
   static constexpr int kBBytes = (kBNMax / 2) * 64 * 2;        // 16 KB (this CTA's half of the first 256 columns)
-  static constexpr int kB2Bytes = WIDE ? 64 * 64 * 2 : 0;      // 8 KB (this CTA's half of columns 256..383)
-  static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutOffset = STAGES * kStageBytes;
   static constexpr int kScaleOffset = kOutOffset + 2 * kEpiBytes;           // float scale[k2MaxN], shift[k2MaxN]
   static constexpr int kBarOffset = kScaleOffset + 2 * k2MaxN * 4;
@@ -593,23 +284,14 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                : "memory");
 }
 
-// WIDE (N in (640, 768], no residual -- the 728-wide pointwise convs): the pair tile is 256 x 384 instead of 256 x 256, so the
-// A rows are fetched twice per M tile instead of three times and a k-block moves 40 KB per CTA for 1.5x the MMA work
-// (the 256-wide tile is L2-throughput-bound).  384 fp32 columns leave no room for a second
-// accumulator stage in the 512 TMEM columns, so the epilogue of a tile does not overlap the next tile's MMAs; the operand ring
-// keeps filling meanwhile.  Columns 256.. come from a second MMA per k-step (UMMA N <= 256) on a second B sub-tile
-// (tmap_b2: 64-row boxes), so accumulator column c is global column n0 + c.
-// MEASURED: correct (passes the model parity suite) but 8 % SLOWER than the 256-wide double-buffered kernel (69.4 vs 64.5 ms
-// of pointwise GEMM per 4096 tiles): losing the epilogue/MMA overlap costs more than the saved operand traffic.  Kept as an
-// experiment switch (BQ_GEMM_WIDE=on), off by default.
-template <int STAGES, bool WIDE>
+template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_b2, const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_out,
                          const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
-  using Plan = SmemPlan2<STAGES, WIDE>;
+  using Plan = SmemPlan2<STAGES>;
   constexpr int BLOCK_K = 64;
-  constexpr int ACC = WIDE ? 1 : kAccStages;
+  constexpr int ACC = kAccStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -631,13 +313,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int n_tiles = (p.N + p.bn_box - 1) / p.bn_box;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const uint32_t b_box_bytes = WIDE ? (uint32_t)Plan::kBBytes : (uint32_t)(p.bn_box / 2) * BLOCK_K * 2;
-  const uint32_t stage_tx = 2u * (Plan::kABytes + b_box_bytes + Plan::kB2Bytes);     // both CTAs' bytes land on the leader's barrier
+  const uint32_t b_box_bytes = (uint32_t)(p.bn_box / 2) * BLOCK_K * 2;
+  const uint32_t stage_tx = 2u * (Plan::kABytes + b_box_bytes);     // both CTAs' bytes land on the leader's barrier
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (WIDE) tma_prefetch_desc(&tmap_b2);
     tma_prefetch_desc(&tmap_out);
     if (p.residual) tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
@@ -668,10 +349,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int n0 = (tile % n_tiles) * p.bn_box;
         int n_cols = p.N - n0;
         if (n_cols > p.bn_box) n_cols = p.bn_box;
-        n_cols = WIDE ? ((n_cols + 31) & ~31) : ((n_cols + 15) & ~15);
-        // this CTA's half of the N tile (WIDE: of its first 256 columns, and of the columns from 256 on)
-        const int nb0 = WIDE ? n0 + (int)rank * 128 : n0 + (int)rank * (n_cols / 2);
-        const int nb1 = n0 + 256 + (int)rank * ((n_cols - 256) / 2);
+        n_cols = (n_cols + 15) & ~15;
+        const int nb0 = n0 + (int)rank * (n_cols / 2);          // this CTA's half of the N tile
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (is_leader) mbar_expect_tx(full_bar(s), stage_tx);
@@ -679,7 +358,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t a_dst = smem_base + s * Plan::kStageBytes, b_dst = a_dst + Plan::kABytes;
           tma_load_2d_2cta(a_dst, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
           tma_load_2d_2cta(b_dst, &tmap_b, full_bar(s), kb * BLOCK_K, nb0);
-          if (WIDE) tma_load_2d_2cta(b_dst + Plan::kBBytes, &tmap_b2, full_bar(s), kb * BLOCK_K, nb1);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -693,9 +371,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int n0 = (tile % n_tiles) * p.bn_box;
         int n_cols = p.N - n0;
         if (n_cols > p.bn_box) n_cols = p.bn_box;
-        n_cols = WIDE ? ((n_cols + 31) & ~31) : ((n_cols + 15) & ~15);
-        const uint32_t idesc = make_idesc(2 * kBM, WIDE ? 256 : n_cols);
-        const uint32_t idesc2 = make_idesc(2 * kBM, WIDE ? n_cols - 256 : 16);
+        n_cols = (n_cols + 15) & ~15;
+        const uint32_t idesc = make_idesc(2 * kBM, n_cols);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBNMax);
 #pragma unroll 1
@@ -706,21 +383,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           int ksteps = BLOCK_K / 16;
           if (kb == num_kb - 1) ksteps = (p.K - kb * BLOCK_K + 15) / 16;
           const uint64_t da = make_smem_desc<128>(a_src), db = make_smem_desc<128>(b_src);
-          const uint64_t db2 = make_smem_desc<128>(b_src + Plan::kBBytes);
           if (elect_one()) {
             umma_bf16_2cta(d_tmem, da, db, idesc, kb ? 1u : 0u);
-            if (WIDE) umma_bf16_2cta(d_tmem + 256u, da, db2, idesc2, kb ? 1u : 0u);
             if (ksteps > 1) {
               umma_bf16_2cta(d_tmem, da + 2u, db + 2u, idesc, 1u);
-              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 2u, db2 + 2u, idesc2, 1u);
             }
             if (ksteps > 2) {
               umma_bf16_2cta(d_tmem, da + 4u, db + 4u, idesc, 1u);
-              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 4u, db2 + 4u, idesc2, 1u);
             }
             if (ksteps > 3) {
               umma_bf16_2cta(d_tmem, da + 6u, db + 6u, idesc, 1u);
-              if (WIDE) umma_bf16_2cta(d_tmem + 256u, da + 6u, db2 + 6u, idesc2, 1u);
             }
             umma_commit_2cta(empty_bar(s));
             if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(as));

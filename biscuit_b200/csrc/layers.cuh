@@ -100,8 +100,11 @@ tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, flo
 // ---------------------------------------------------------------------------------------------------
 constexpr int kC1Tile = 16;
 constexpr int kC1In = 2 * kC1Tile + 1;
+// TIn = uint8_t: raw RGB, standardised here with the tile's (mean, 1/std).  TIn = float: the caller already applied
+// tf.image.per_image_standardization (the reference's literal call, results.py:255-257) -- values are used as they are.
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, const float* __restrict__ inv_std,
+conv1_kernel(const TIn* __restrict__ tiles, const float* __restrict__ mean, const float* __restrict__ inv_std,
              const float* __restrict__ w /*[27][32]*/, const float* __restrict__ scale, const float* __restrict__ shift,
              bf16* __restrict__ out, int in_px, int out_px) {
   __shared__ float patch[kC1In * kC1In * 3];
@@ -109,8 +112,9 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
   __shared__ float sc[32], sh[32];
   const int img = blockIdx.z;
   const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
-  const float mu = mean[img], is = inv_std[img];
-  const uint8_t* src = tiles + (int64_t)img * in_px * in_px * 3;
+  constexpr bool kRaw = sizeof(TIn) == 1;
+  const float mu = kRaw ? mean[img] : 0.f, is = kRaw ? inv_std[img] : 1.f;
+  const TIn* src = tiles + (int64_t)img * in_px * in_px * 3;
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 32) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
   const int iy0 = oy0 * 2, ix0 = ox0 * 2;
@@ -118,7 +122,10 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
     const int r = i / (kC1In * 3), rem = i - r * (kC1In * 3);
     const int y = iy0 + r, xc = ix0 * 3 + rem;
     float v = 0.f;
-    if (y < in_px && xc < in_px * 3) v = __fmul_rn(__fadd_rn((float)src[(int64_t)y * in_px * 3 + xc], -mu), is);
+    if (y < in_px && xc < in_px * 3) {
+      const float raw = (float)src[(int64_t)y * in_px * 3 + xc];
+      v = kRaw ? __fmul_rn(__fadd_rn(raw, -mu), is) : raw;
+    }
     patch[i] = v;
   }
   __syncthreads();
@@ -160,164 +167,6 @@ conv1_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ mean, 
       f[j] = fmaxf(__fadd_rn(__fmul_rn(acc[c], sc[c]), sh[c]), 0.f);
     }
     *(uint4*)(o + g * 8) = float_to_bf16x8(f);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// depthwise 3x3, stride 1, 'same' (zero pad 1).  One thread = one pixel x 8 channels (16 B).
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-depthwise3x3_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][C]*/, bf16* __restrict__ out,
-                    int n_img, int H, int W, int C, int relu_in) {
-  const int cv = C >> 3;
-  const int64_t total = (int64_t)n_img * H * W * cv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv);
-    int64_t pix = idx / cv;
-    const int x = (int)(pix % W);
-    pix /= W;
-    const int y = (int)(pix % H);
-    const int img = (int)(pix / H);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const bf16* base = in + ((int64_t)img * H * W) * C + c8 * 8;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const uint4 v = __ldg((const uint4*)(base + ((int64_t)yy * W + xx) * C));
-        float f[8];
-        bf16x8_to_float(v, f);
-        const float4 w0 = __ldg((const float4*)(w + (ky * 3 + kx) * C + c8 * 8));
-        const float4 w1 = __ldg((const float4*)(w + (ky * 3 + kx) * C + c8 * 8 + 4));
-        const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xv = relu_in ? fmaxf(f[j], 0.f) : f[j];
-          acc[j] = fmaf(xv, wf[j], acc[j]);
-        }
-      }
-    }
-    *(uint4*)(out + (((int64_t)img * H + y) * W + x) * C + c8 * 8) = float_to_bf16x8(acc);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// depthwise 3x3, second generation (BQ_DW=v2; superseded by dwpipe_sm100.cuh): shared-memory staged, register sliding window.
-// One block = (image, 19x19 pixel tile, chunk of CC channels).  The (TH+2)x(TW+2) halo tile is loaded ONCE with
-// 16-byte coalesced loads (4 in flight per thread; optional ReLU applied here, once per element).  A thread
-// owns (4 channels, one tile column) and walks DOWN the column keeping the 3x3 window in registers: per 4
-// outputs it issues 3 LDS.64 + 36 FMA (weights: 36 registers) and one 8-byte store; the stores of a warp form
-// full 112/128-byte lines per pixel.  Global->SM traffic is (21/19)^2 = 1.22x the tensor (1.0x for the 19x19
-// middle flow) instead of ~5x for the first-generation kernel above.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kDwTile = 19;
-constexpr int kDwHalo = kDwTile + 2;
-// three horizontally adjacent pixels x 4 channels, widened to fp32 as two float2 pairs (for FFMA2)
-__device__ __forceinline__ void dw_load3(const bf16* row, int CC, float2 (&d)[3][2]) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const uint2 v = *(const uint2*)(row + (size_t)k * CC);
-    d[k][0] = make_float2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u));
-    d[k][1] = make_float2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
-  }
-}
-__global__ void __launch_bounds__(320)
-depthwise3x3_smem_kernel(const __grid_constant__ CUtensorMap tmap_in /*4-D [C, W, H, N], box [CC, 21, 21, 1]*/,
-                         const float* __restrict__ w /*[9][C]*/, bf16* __restrict__ out, int H, int W, int C,
-                         int CC /*channels per block: 64 or 56*/, int tiles_x, int relu_in) {
-  extern __shared__ __align__(128) uint8_t dw_smem[];
-  __shared__ __align__(8) uint64_t fill_bar;
-  bf16* tile = (bf16*)dw_smem;                       // [kDwHalo][kDwHalo][CC]
-  const int cpc = CC >> 2;                           // 4-channel groups per pixel
-  const int c0 = blockIdx.x * CC;
-  const int ty0 = (blockIdx.y / tiles_x) * kDwTile, tx0 = (blockIdx.y % tiles_x) * kDwTile;
-  const int img = blockIdx.z;
-  // ---- fill: ONE TMA tile load per block; the halo outside the image is zero-filled by the TMA unit
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&fill_bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                 "r"((uint32_t)(kDwHalo * kDwHalo * CC * 2))
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"((uint32_t)__cvta_generic_to_shared(tile)), "l"((uint64_t)&tmap_in), "r"(bar), "r"(c0), "r"(tx0 - 1),
-          "r"(ty0 - 1), "r"(img)
-        : "memory");
-  }
-  const int c4 = threadIdx.x % cpc, px = threadIdx.x / cpc;      // blockDim = cpc * kDwTile
-  const int th = min(kDwTile, H - ty0), tw = min(kDwTile, W - tx0);
-  const bool active = px < tw;
-  float2 wr[9][2];                                               // 9 taps x 4 channels as float2 pairs
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 wv = __ldg((const float4*)(w + (int64_t)t * C + c0 + c4 * 4));
-      wr[t][0] = make_float2(wv.x, wv.y);
-      wr[t][1] = make_float2(wv.z, wv.w);
-    }
-  }
-  __syncthreads();                                               // barrier initialised before anyone polls it
-  {
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(0x989680u)
-          : "memory");
-    }
-  }
-  if (relu_in) {                                                 // ReLU once per element, in place
-    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
-    const int total_vec = kDwHalo * kDwHalo * CC / 8;
-    for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
-      uint4 v = *(uint4*)(tile + (size_t)i * 8);
-      __nv_bfloat162* b = (__nv_bfloat162*)&v;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = __hmax2(b[j], z2);
-      *(uint4*)(tile + (size_t)i * 8) = v;
-    }
-    __syncthreads();
-  }
-  if (!active) return;
-  const bf16* col = tile + (size_t)px * CC + c4 * 4;             // halo column px (= image column px - 1)
-  const size_t row_stride = (size_t)kDwHalo * CC;
-  bf16* dst = out + ((int64_t)img * H * W + (int64_t)ty0 * W + tx0 + px) * C + c0 + c4 * 4;
-  float2 ra[3][2], rb[3][2], rc[3][2];                           // rolling window rows (static register names)
-  dw_load3(col, CC, ra);
-  dw_load3(col + row_stride, CC, rb);
-  // packed fp32x2 FMAs (Blackwell FFMA2): two channels per instruction, each lane an ordinary RN fma, so the
-  // result is bit-identical to 36 scalar fmaf in the same tap order
-  auto step = [&](const float2 (&r0)[3][2], const float2 (&r1)[3][2], float2 (&r2)[3][2], int py) {
-    dw_load3(col + (size_t)(py + 2) * row_stride, CC, r2);
-    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r0[kx][0], wr[kx][0], a0); a1 = __ffma2_rn(r0[kx][1], wr[kx][1], a1); }
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r1[kx][0], wr[3 + kx][0], a0); a1 = __ffma2_rn(r1[kx][1], wr[3 + kx][1], a1); }
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) { a0 = __ffma2_rn(r2[kx][0], wr[6 + kx][0], a0); a1 = __ffma2_rn(r2[kx][1], wr[6 + kx][1], a1); }
-    uint2 o;
-    __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-    ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
-    ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
-    *(uint2*)(dst + (int64_t)py * W * C) = o;
-  };
-  for (int py = 0; py < th; py += 3) {
-    step(ra, rb, rc, py);
-    if (py + 1 < th) step(rb, rc, ra, py + 1);
-    if (py + 2 < th) step(rc, ra, rb, py + 2);
   }
 }
 
@@ -468,76 +317,6 @@ mc_expand_kernel(const bf16* __restrict__ h, bf16* __restrict__ a2, int n, int T
   }
 }
 
-// Final stage, one block per tile: for every sample t, logits = ((keep .* h2[i,t,:]) @ W3) * alpha + b3,
-// softmax (2 classes... n_classes <= 8), then warp-shuffle reductions give the mean and the population std
-// over the T samples (two-pass: mean first, then sum of squared deviations).
 constexpr int kMaxClasses = 8;
-__global__ void __launch_bounds__(256)
-head_final_kernel(const bf16* __restrict__ h2 /*[n*T, width]*/, const float* __restrict__ w3 /*[width][C]*/,
-                  const float* __restrict__ b3, int T, int width, int n_classes, float alpha, int dropout_on,
-                  uint64_t seed, uint64_t tile_base, int site, uint32_t thresh, const uint8_t* __restrict__ masks,
-                  int n_sites, int site_slot, float* __restrict__ mean_out, float* __restrict__ std_out) {
-  extern __shared__ float probs[];   // [T][n_classes]
-  const int i = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < T; t += nwarps) {
-    float acc[kMaxClasses];
-#pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) acc[c] = 0.f;
-    const bf16* row = h2 + ((int64_t)i * T + t) * width;
-    for (int e4 = lane; e4 < (width >> 2); e4 += 32) {
-      uint32_t kb = 0xFu;
-      if (dropout_on) {
-        if (masks) {
-          const uint8_t* mp = masks + (((int64_t)i * T + t) * n_sites + site_slot) * width + e4 * 4;
-          kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
-        } else {
-          kb = keep4(seed, tile_base + (uint64_t)i, t, site, e4, thresh);
-        }
-      }
-      const uint2 v = *(const uint2*)(row + e4 * 4);
-      const __nv_bfloat162* b = (const __nv_bfloat162*)&v;
-      const float2 f01 = __bfloat1622float2(b[0]), f23 = __bfloat1622float2(b[1]);
-      const float x[4] = {(kb & 1u) ? f01.x : 0.f, (kb & 2u) ? f01.y : 0.f, (kb & 4u) ? f23.x : 0.f,
-                          (kb & 8u) ? f23.y : 0.f};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float* wr = w3 + (int64_t)(e4 * 4 + j) * n_classes;
-        for (int c = 0; c < n_classes; ++c) acc[c] = fmaf(x[j], __ldg(wr + c), acc[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
-      for (int o = 16; o; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-    if (lane == 0) {
-      float z[kMaxClasses], mx = -INFINITY;
-      for (int c = 0; c < n_classes; ++c) {
-        z[c] = __fadd_rn(__fmul_rn(acc[c], alpha), b3[c]);
-        mx = fmaxf(mx, z[c]);
-      }
-      float den = 0.f;
-      for (int c = 0; c < n_classes; ++c) { z[c] = expf(z[c] - mx); den += z[c]; }
-      for (int c = 0; c < n_classes; ++c) probs[t * n_classes + c] = z[c] / den;
-    }
-  }
-  __syncthreads();
-  // warp c handles class c: mean then population std over T with warp-shuffle reductions
-  for (int c = warp; c < n_classes; c += nwarps) {
-    float s = 0.f;
-    for (int t = lane; t < T; t += 32) s += probs[t * n_classes + c];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float m = s / (float)T;
-    float d2 = 0.f;
-    for (int t = lane; t < T; t += 32) {
-      const float d = probs[t * n_classes + c] - m;
-      d2 = fmaf(d, d, d2);
-    }
-    for (int o = 16; o; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-    if (lane == 0) {
-      mean_out[(int64_t)i * n_classes + c] = m;
-      std_out[(int64_t)i * n_classes + c] = sqrtf(d2 / (float)T);
-    }
-  }
-}
 
 }  // namespace bq

@@ -16,9 +16,7 @@
 #include "gemm_sm100.cuh"
 #include "layers.cuh"
 #include "head_sm100.cuh"
-#include "dw_sm100.cuh"
 #include "dwpipe_sm100.cuh"
-#include "sepconv_sm100.cuh"
 #include "sepconv2d_sm100.cuh"
 #include "sepmid_sm100.cuh"
 #include "stain_sm100.cuh"
@@ -101,7 +99,6 @@ struct PwWeights {          // a GEMM's B operand + per-channel epilogue
 };
 struct SepWeights {
   DevBuf dw;                // fp32 [9][cin]
-  DevBuf bdiag;             // bf16 [ceil(cin/64)][9 taps][4 groups][16x16 diagonal tile] for the tensor-core depthwise
   PwWeights pw;
 };
 
@@ -193,7 +190,7 @@ int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int 
 // ------------------------------------------------------------------------------------------------
 // execution plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEPFUSED, OP_SEP2D, OP_SEPMID, OP_PADCOPY };
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEP2D, OP_SEPMID, OP_PADCOPY };
 
 struct Op {
   OpKind kind;
@@ -206,8 +203,6 @@ struct Op {
   int H = 0, W = 0, C = 0, Ho = 0, Wo = 0, Cout = 0;
   int relu_in = 0, pad_top = 0, pad_left = 0;
   const float* dw = nullptr;
-  const bf16* bdiag = nullptr;
-  bq::sepf::SepParams sp;     // OP_SEPFUSED
   bq::sep2d::Sep2dParams s2;  // OP_SEP2D
   bq::sepmid::SepMidParams sm; // OP_SEPMID
   int to_padded = 0;          // OP_PADCOPY direction
@@ -218,7 +213,6 @@ struct Op {
   int blk_k = 64;
   CUtensorMap ta, tb, tc, tr; // A, B, output, residual
   CUtensorMap tb2;            // B with a half-height box (2-CTA kernel: each CTA stages N/2 rows)
-  CUtensorMap tb3;            // B with a 64-row box (WIDE 2-CTA kernel: columns 256.. of a 384-wide tile)
 };
 
 struct Arena {                // activation scratch: a handful of max-size buffers
@@ -232,25 +226,15 @@ struct bq_model {
   bq_ctx* ctx = nullptr;
   bq_model_config cfg{};
   bool weights_loaded = false;
-  bool use_simt = false;
-  int dw_mode = 3;                             // 3: persistent TMA-pipelined (default), 1: one tile per block, 2: tensor-core, 0: first generation
-  bool gemm_direct_epi = false;
-  bool gemm_2cta = true;
-  bool head_fused = true;
+  bool use_simt = false;                       // BQ_GEMM=simt: plain CUDA-core GEMM instead of tcgen05 (debug oracle, never the default)
   // The launch sequence of a full micro-batch after block1_conv1 is static (fixed arena addresses, tensor maps by
   // value): it is captured once into a CUDA graph and replayed, which removes ~90 stream launches per micro-batch
   // from the host and shortens the gaps between dependent kernels (BQ_GRAPH=off: plain stream launches).
   bool use_graph = true;
   cudaGraphExec_t backbone_graph = nullptr;
   int64_t graph_kernels = 0;                   // kernel launches one replay stands for (bq_launch_count bookkeeping)
-  bool gemm_wide = false;                      // experiment: 256 x 384 pair tiles for the 728-wide pointwise convs (BQ_GEMM_WIDE=on); slower
-  bool sep2d = true;                           // fused 2-D-patch sepconv for the K <= 256, N <= 256 entry-flow layers (BQ_SEP2D=off)
-  bool dw_cc32 = false;                        // 32-channel depthwise blocks (more blocks per SM) for C % 64 == 0 layers
-  bool sep_fused = false;                      // experiment: fused depthwise->pointwise kernel for the 728->728 layers (BQ_SEPCONV=fused)
-  bool conv2_is = true;                        // input-stationary block1_conv2 (BQ_CONV2=taps selects the per-tap reload kernel)
   bool sep_mid = true;                         // fused depthwise->pointwise kernel on the zero-padded layout for the 728-wide middle flow (BQ_SEPMID=off)
   DevBuf midbuf[4];                            // dedicated zero-bordered [max_batch * 400 (+ slack), 728] activation buffers of the middle flow
-  int entry_batch = 0;                         // tiles per entry-flow sub-batch (L2-resident intermediates)
   int max_batch = 0;
   int px = 299;
 
@@ -265,6 +249,8 @@ struct bq_model {
   // buffers
   DevBuf tiles_dev;                            // uint8 staging [max_batch, px, px, 3] (double-buffered with tiles_dev2)
   DevBuf tiles_dev2;
+  DevBuf tiles_f32[2];                         // float32 staging for already-standardised host tiles (allocated on first use)
+  bool input_f32 = false;                      // the current call feeds standardised float tiles: no statistics, no normaliser
   int norm_kind = 0;                           // BQ_NORM_*: stain normalisation in front of the tile statistics
   float norm_means[3] = {0, 0, 0}, norm_stds[3] = {1, 1, 1};
   DevBuf tiles_norm, norm_lut, norm_stats;     // normalised micro-batch, gamma table, per-tile LAB statistics
@@ -337,7 +323,7 @@ void kprofile_collect(bq_model* m) {
 }
 
 int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                const CUtensorMap& tr, int blk_k, const CUtensorMap* tb_half = nullptr, const CUtensorMap* tb_q = nullptr) {
+                const CUtensorMap& tr, int blk_k, const CUtensorMap* tb_half = nullptr) {
   bq_ctx* ctx = m->ctx;
   if (gp.M <= 0) return BQ_OK;
   if (m->use_simt) {
@@ -349,36 +335,22 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
   using namespace bq::sm100;
   const int m_tiles = (gp.M + kBM - 1) / kBM;
   const int n_tiles = (gp.N + gp.bn_box - 1) / gp.bn_box;
-  int grid = m_tiles * n_tiles;
-  if (grid > ctx->num_sms) grid = ctx->num_sms;
-  if (blk_k == 32 && m->conv2_is && gp.conv_mode && gp.N == 64 && gp.K == 288 && 2 * gp.in_w + 2 + 128 <= kC2WinRows) {
-    int g2 = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
+  if (blk_k == 32) {
+    // block1_conv2: input-stationary implicit GEMM
+    if (!(gp.conv_mode && gp.N == 64 && gp.K == 288 && 2 * gp.in_w + 2 + 128 <= kC2WinRows))
+      return bq_fail(ctx, BQ_ERR_ARG, "conv3x3_is_kernel: unsupported geometry");
+    const int g2 = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
     conv3x3_is_kernel<<<g2, kC2Threads, kC2Smem, ctx->stream>>>(ta, tb, gp);
-  } else if (blk_k == 32) {
-    gemm_tcgen05_kernel<32, false><<<grid, kThreads, SmemPlan<32, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
-  } else if (m->gemm_2cta && tb_half && gp.bn_box % 32 == 0 && gp.N <= k2MaxN) {
-    const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
-    int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
-    // a deeper operand ring where no residual staging is needed (the ring is what hides the DRAM round trip of A)
-    if (gp.residual) {
-      gemm_tcgen05_2cta_kernel<k2Stages, false><<<2 * clusters, k2Threads, SmemPlan2<k2Stages>::kTotal, ctx->stream>>>(
-          ta, *tb_half, *tb_half, tc, tr, gp);
-    } else if (m->gemm_wide && tb_q && gp.bn_box == 256 && gp.N > 640 && gp.N <= 2 * k2WideN) {
-      // 728-wide pointwise convs: two 256 x 384 pair tiles per M tile instead of three 256 x 256 ones
-      GemmParams gw = gp;
-      gw.bn_box = k2WideN;
-      const int wide_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * 2;
-      const int wc = wide_tiles < ctx->num_sms / 2 ? wide_tiles : ctx->num_sms / 2;
-      gemm_tcgen05_2cta_kernel<k2Stages, true><<<2 * wc, k2Threads, SmemPlan2<k2Stages, true>::kTotalNoRes, ctx->stream>>>(
-          ta, *tb_half, *tb_q, tc, tr, gw);
-    } else {
-      gemm_tcgen05_2cta_kernel<k2Stages + 1, false><<<2 * clusters, k2Threads, SmemPlan2<k2Stages + 1>::kTotalNoRes, ctx->stream>>>(
-          ta, *tb_half, *tb_half, tc, tr, gp);
-    }
-  } else if (m->gemm_direct_epi) {
-    gemm_tcgen05_kernel<64, false><<<grid, kThreads, SmemPlan<64, false>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
   } else {
-    gemm_tcgen05_kernel<64, true><<<grid, kThreads, SmemPlan<64, true>::kTotal, ctx->stream>>>(ta, tb, tc, tr, gp);
+    if (!tb_half || gp.bn_box % 32 != 0 || gp.N > k2MaxN)
+      return bq_fail(ctx, BQ_ERR_ARG, "gemm_tcgen05_2cta_kernel: unsupported N = %d (tile %d)", gp.N, gp.bn_box);
+    const int pair_tiles = ((gp.M + 2 * kBM - 1) / (2 * kBM)) * n_tiles;
+    const int clusters = pair_tiles < ctx->num_sms / 2 ? pair_tiles : ctx->num_sms / 2;
+    // a deeper operand ring where no residual staging is needed (the ring is what hides the DRAM round trip of A)
+    if (gp.residual)
+      gemm_tcgen05_2cta_kernel<k2Stages><<<2 * clusters, k2Threads, SmemPlan2<k2Stages>::kTotal, ctx->stream>>>(ta, *tb_half, tc, tr, gp);
+    else
+      gemm_tcgen05_2cta_kernel<k2Stages + 1><<<2 * clusters, k2Threads, SmemPlan2<k2Stages + 1>::kTotalNoRes, ctx->stream>>>(ta, *tb_half, tc, tr, gp);
   }
   BQ_LAUNCH_CHECK(ctx);
   return BQ_OK;
@@ -418,7 +390,6 @@ int make_gemm(bq_model* m, Op& op, const bf16* a, int rows_per_tile, const PwWei
   op.tr = op.tc;
   if (residual && (rc = make_tmap(m->ctx, &op.tr, residual, (uint64_t)g.M, (uint64_t)w.cout, (uint64_t)w.cout, 128, 64))) return rc;
   if ((rc = make_tmap(m->ctx, &op.tb2, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, g.bn_box / 2, 64))) return rc;
-  if ((rc = make_tmap(m->ctx, &op.tb3, w.w.p, (uint64_t)w.cout, (uint64_t)w.ktot, (uint64_t)w.ktot, 64, 64))) return rc;
   return BQ_OK;
 }
 
@@ -426,7 +397,7 @@ int build_plan(bq_model* m) {
   bq_ctx* ctx = m->ctx;
   const int B = m->max_batch;
   // the fused head is launched once per `head_batch` tiles so that it has >= 148 four-tile groups to spread over the SMs
-  m->head_batch = m->head_fused ? ((592 + B - 1) / B) * B : B;
+  m->head_batch = ((592 + B - 1) / B) * B;
   if (m->head_batch < B) m->head_batch = B;
   const int px = m->px;
   const int s1 = (px - 3) / 2 + 1;        // 149
@@ -467,7 +438,7 @@ int build_plan(bq_model* m) {
     g.b_ptr = (const bf16*)m->conv2.w.p; g.ldb = 288;
     if ((rc = make_tmap(ctx, &op.ta, A.p(0), (uint64_t)s1 * s1 * B, 32, 32, 128, 32))) return rc;
     if ((rc = make_tmap(ctx, &op.tb, m->conv2.w.p, 64, 288, 288, 64, 32))) return rc;
-    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb; op.tb3 = op.tb;      // unused by the direct-store epilogue
+    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb;      // unused by the direct-store epilogue
     op.Ho = s2; op.Wo = s2; op.Cout = 64;
     m->plan.push_back(op);
   }
@@ -479,14 +450,9 @@ int build_plan(bq_model* m) {
   auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
     Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
     op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
-    const int CC = (c % 64 != 0) ? 56 : (m->dw_cc32 ? 32 : 64);
-    int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::kDwHalo, bq::kDwHalo, CC);
+    const int CC = (c % 64 != 0) ? 56 : 64;                            // 728 = 13 x 56
+    int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwp::kHalo, bq::dwp::kHalo, CC);
     if (r && !dw_rc) dw_rc = r;
-    r = make_tmap_nhwc(ctx, &op.tb, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kHalo, bq::dwtc::kHalo, 64, true);
-    if (r && !dw_rc) dw_rc = r;
-    r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwtc::kTile, bq::dwtc::kTile, 64, true);
-    if (r && !dw_rc) dw_rc = r;
-    op.bdiag = (const bf16*)sw.bdiag.p;
     op.tag = "dw" + std::to_string(n_dw++);          // debug-stage name of the n-th stand-alone depthwise output
     op.Ho = h; op.Wo = h; op.Cout = c;
     m->plan.push_back(op);
@@ -504,25 +470,7 @@ int build_plan(bq_model* m) {
   // one SeparableConv2D (+BN, optional ReLU / residual): fused kernel for 728->728, otherwise depthwise + GEMM
   auto add_sep = [&](const bf16* in, bf16* dw_tmp, int h, int cin, int relu_in, const SepWeights& sw, bf16* out, int relu_out,
                      const bf16* resid, int stage, const char* tag) -> int {
-    if (m->sep_fused && cin == 728 && sw.pw.cout == 728 && 2 * (h + 1) + 130 <= bq::sepf::kPatchRows) {
-      Op op; op.kind = OP_SEPFUSED; op.stage = stage;
-      if (tag) op.tag = tag;
-      op.in = in; op.out = out; op.in2 = resid; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = 728;
-      op.rows_per_tile = h * h;
-      op.sp.M = h * h * B; op.sp.H = h; op.sp.W = h; op.sp.C = cin; op.sp.relu_in = relu_in; op.sp.relu_out = relu_out;
-      op.sp.has_res = resid != nullptr;
-      op.sp.dw = (const float*)sw.dw.p; op.sp.scale = (const float*)sw.pw.scale.p; op.sp.shift = (const float*)sw.pw.shift.p;
-      const uint64_t rows = (uint64_t)h * h * B;
-      int r;
-      if ((r = make_tmap(ctx, &op.ta, in, rows, 728, 728, bq::sepf::kPatchRows, 64))) return r;
-      if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, 728, 728, 728, 128, 64))) return r;
-      if ((r = make_tmap(ctx, &op.tc, out, rows, 728, 728, 128, 64))) return r;
-      op.tr = op.tc;
-      if (resid && (r = make_tmap(ctx, &op.tr, resid, rows, 728, 728, 128, 64))) return r;
-      m->plan.push_back(op);
-      return BQ_OK;
-    }
-    if (m->sep2d && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
+    if (!m->use_simt && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
       Op op; op.kind = OP_SEP2D; op.stage = stage;
       if (tag) op.tag = tag;
       op.in = in; op.out = out; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = sw.pw.cout;
@@ -639,6 +587,7 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
   const double act = 2.0;   // bytes per bf16 activation element
   switch (op.kind) {
     case OP_STATS: {
+      if (m->input_f32) return BQ_OK;              // standardised by the caller
       KScope ks(m, BQ_K_STATS, 0, (double)nb * px * px * 3);
       bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>(m->tiles_src, (int64_t)px * px * 3,
                                                         (float*)m->mean.p, (float*)m->inv_std.p);
@@ -647,10 +596,16 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
     case OP_CONV1: {
       KScope ks(m, BQ_K_CONV1, 2.0 * nb * op.Ho * op.Ho * 27 * 32, (double)nb * px * px * 3 + act * nb * op.Ho * op.Ho * 32);
       dim3 grid((op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, (op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, nb);
-      bq::conv1_kernel<<<grid, 256, 0, ctx->stream>>>(m->tiles_src, (const float*)m->mean.p,
-                                                     (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
-                                                     (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
-                                                     op.out, px, op.Ho);
+      if (m->input_f32)
+        bq::conv1_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)m->tiles_src, (const float*)m->mean.p,
+                                                              (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
+                                                              (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
+                                                              op.out, px, op.Ho);
+      else
+        bq::conv1_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m->tiles_src, (const float*)m->mean.p,
+                                                                (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
+                                                                (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
+                                                                op.out, px, op.Ho);
       break;
     }
     case OP_GEMM: {
@@ -661,42 +616,20 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       const double kin = g.conv_mode ? g.K / 9 : g.K;
       KScope ks(m, g.conv_mode ? BQ_K_GEMM_CONV2 : BQ_K_GEMM_PW, 2.0 * rows_out * g.N * g.K,
                 act * ((double)g.M * kin + rows_out * g.N * (g.residual ? 2 : 1) + (double)g.N * g.K));
-      return launch_gemm(m, g, op.ta, op.tb, op.tc, op.tr, op.blk_k, g.conv_mode ? nullptr : &op.tb2, g.conv_mode ? nullptr : &op.tb3);
+      return launch_gemm(m, g, op.ta, op.tb, op.tc, op.tr, op.blk_k, g.conv_mode ? nullptr : &op.tb2);
     }
     case OP_DW: {
       KScope ks(m, BQ_K_DW, 2.0 * 9 * nb * op.H * op.W * op.C, 2 * act * nb * op.H * op.W * op.C);
-      if (m->dw_mode == 2) {
-        const int tiles = (op.H + bq::dwtc::kTile - 1) / bq::dwtc::kTile;
-        const int chunks = (op.C + 63) / 64;
-        int per_chunk = ctx->num_sms / chunks;                       // CTAs per channel chunk (persistent)
-        const int items = nb * tiles * tiles;
-        if (per_chunk > items) per_chunk = items;
-        if (per_chunk < 1) per_chunk = 1;
-        bq::dwtc::depthwise3x3_tc_kernel<<<chunks * per_chunk, bq::dwtc::kThreads, bq::dwtc::kSmem, ctx->stream>>>(
-            op.tb, op.tc, op.bdiag, nb, op.H, op.W, op.C, tiles, chunks, op.relu_in);
-      } else if (m->dw_mode == 0) {
-        bq::depthwise3x3_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(
-            op.in, op.dw, op.out, nb, op.H, op.W, op.C, op.relu_in);
-      } else if (m->dw_mode == 3) {
-        const int CC = (op.C % 64 != 0) ? 56 : 64;                        // 728 = 13 x 56
-        const int tiles = (op.H + bq::dwp::kTile - 1) / bq::dwp::kTile;
-        const int64_t items = (int64_t)nb * tiles * tiles * (op.C / CC);
-        const int grid = (int)std::min<int64_t>(items, ctx->num_sms);
+      const int CC = (op.C % 64 != 0) ? 56 : 64;                        // 728 = 13 x 56
+      const int tiles = (op.H + bq::dwp::kTile - 1) / bq::dwp::kTile;
+      const int64_t items = (int64_t)nb * tiles * tiles * (op.C / CC);
+      const int grid = (int)std::min<int64_t>(items, ctx->num_sms);
 #define BQ_DWP_LAUNCH(RELU, CCV)                                                                              \
   bq::dwp::depthwise3x3_pipe_kernel<RELU, CCV><<<grid, bq::dwp::kThreads, bq::dwp::kSmem, ctx->stream>>>(    \
       op.ta, op.dw, op.out, nb, op.H, op.W, op.C, tiles)
-        if (CC == 56) { if (op.relu_in) BQ_DWP_LAUNCH(true, 56); else BQ_DWP_LAUNCH(false, 56); }
-        else          { if (op.relu_in) BQ_DWP_LAUNCH(true, 64); else BQ_DWP_LAUNCH(false, 64); }
+      if (CC == 56) { if (op.relu_in) BQ_DWP_LAUNCH(true, 56); else BQ_DWP_LAUNCH(false, 56); }
+      else          { if (op.relu_in) BQ_DWP_LAUNCH(true, 64); else BQ_DWP_LAUNCH(false, 64); }
 #undef BQ_DWP_LAUNCH
-      } else {
-        const int CC = (op.C % 64 != 0) ? 56 : (m->dw_cc32 ? 32 : 64);   // 728 = 13 x 56
-        const int tiles = (op.H + bq::kDwTile - 1) / bq::kDwTile;
-        dim3 grid((op.C + CC - 1) / CC, tiles * tiles, nb);
-        const int threads = (CC / 4) * bq::kDwTile;
-        const size_t smem = (size_t)bq::kDwHalo * bq::kDwHalo * CC * sizeof(bf16);
-        bq::depthwise3x3_smem_kernel<<<grid, threads, smem, ctx->stream>>>(op.ta, op.dw, op.out, op.H, op.W, op.C, CC,
-                                                                        tiles, op.relu_in);
-      }
       break;
     }
     case OP_POOLADD: {
@@ -709,16 +642,6 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.Ho * op.Wo * op.C);
       bq::subsample2_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
           op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C);
-      break;
-    }
-    case OP_SEPFUSED: {
-      bq::sepf::SepParams sp = op.sp;
-      sp.M = op.rows_per_tile * nb;
-      const int items = ((sp.M + 127) / 128) * 2;
-      const int grid = items < ctx->num_sms ? items : ctx->num_sms;
-      const double px_n = (double)sp.M;
-      KScope ks(m, BQ_K_SEP_FUSED, 2.0 * px_n * sp.C * (sp.C + 9.0), act * px_n * sp.C * (sp.has_res ? 3.0 : 2.0));
-      bq::sepf::sepconv_fused_kernel<<<grid, bq::sepf::kThreads, bq::sepf::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sp);
       break;
     }
     case OP_SEP2D: {
@@ -772,35 +695,10 @@ int stage_tiles(bq_model* m, const uint8_t* tiles, int nb) {
   return BQ_OK;
 }
 
-// The entry flow (block1..block4: 147^2..37^2 maps, 5.5 MB of activations per tile and layer) runs in SUB-batches of
-// `entry_batch` tiles that reuse the same arena addresses, so its intermediates stay L2-resident (126 MB) instead of
-// streaming through HBM; the middle / exit flow (19^2 maps, 0.5 MB per tile) runs on the whole micro-batch so that its
-// GEMMs have enough tiles to fill the 74 CTA pairs.
+// One micro-batch through the plan as plain stream launches (profiling, debug stops, partial micro-batches).
 int run_backbone(bq_model* m, int nb, const std::string* stop_tag, const Op** stopped) {
-  const size_t tile_bytes = (size_t)m->px * m->px * 3;
-  const uint8_t* src0 = m->tiles_src;
-  size_t entry_end = 0;
-  while (entry_end < m->plan.size() && m->plan[entry_end].stage <= 2) ++entry_end;
-  const int EB = (stop_tag || m->entry_batch <= 0 || m->entry_batch > nb) ? nb : m->entry_batch;
   int cur_stage = -1;
-  for (int sub0 = 0; sub0 < nb; sub0 += EB) {
-    const int nsub = (nb - sub0 < EB) ? (nb - sub0) : EB;
-    m->tiles_src = src0 + (size_t)sub0 * tile_bytes;
-    for (size_t i = 0; i < entry_end; ++i) {
-      Op& op = m->plan[i];
-      if (m->profiling && sub0 == 0 && op.stage != cur_stage) {
-        cudaEventRecord(m->ev[op.stage], m->ctx->stream);
-        cur_stage = op.stage;
-      }
-      // the last entry op (block4 pool+add) scatters each sub-batch to its rows of the full micro-batch tensor
-      const int64_t out_off = (i + 1 == entry_end) ? (int64_t)sub0 * op.Ho * op.Wo * op.C : 0;
-      int rc = run_op(m, op, nsub, out_off);
-      if (rc) { m->tiles_src = src0; return rc; }
-      if (stop_tag && op.tag == *stop_tag) { if (stopped) *stopped = &op; m->tiles_src = src0; return BQ_OK; }
-    }
-  }
-  m->tiles_src = src0;
-  for (size_t i = entry_end; i < m->plan.size(); ++i) {
+  for (size_t i = 0; i < m->plan.size(); ++i) {
     Op& op = m->plan[i];
     if (m->profiling && op.stage != cur_stage) {
       cudaEventRecord(m->ev[op.stage], m->ctx->stream);
@@ -820,7 +718,7 @@ int run_backbone_graphed(bq_model* m, int nb) {
   bq_ctx* ctx = m->ctx;
   size_t first = 0;
   while (first < m->plan.size() && (m->plan[first].kind == OP_STATS || m->plan[first].kind == OP_CONV1)) ++first;
-  const bool ok = m->use_graph && !m->profiling && nb == m->max_batch && m->entry_batch <= 0 && first > 0 && first < m->plan.size();
+  const bool ok = m->use_graph && !m->profiling && nb == m->max_batch && first > 0 && first < m->plan.size();
   if (!ok) return run_backbone(m, nb, nullptr, nullptr);
   int rc;
   for (size_t i = 0; i < first; ++i)
@@ -907,82 +805,52 @@ int run_head(bq_model* m, int nb, int T, uint64_t seed, uint64_t tile_base, cons
     const int64_t cap = (int64_t)ctx->num_sms * 32;
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
   };
-  const bool fused = m->head_fused && Hn == 2 && Wd <= bq::head::kHMaxW && Wd % 64 == 0;
-  for (int i = 0; i < Hn; ++i) {
-    auto& hg = m->head_gemms[i];
+  if (Hn != 2 || Wd > bq::head::kHMaxW || Wd % 64) return bq_fail(ctx, BQ_ERR_ARG, "the fused MC-dropout head needs 2 hidden layers of width <= 1024 (hp.py:13,21)");
+  if (nb > 0) {
+    // ---- hidden_0 of this micro-batch (GEMM kernel), written at row h1_off of the head buffer
+    auto& hg = m->head_gemms[0];
     GemmParams g = hg.gp;
-    if (i == 0) {
-      if (nb == 0) continue;
-      if (m->sites & 1) {
-        // dropout on the pooled features: one masked copy of the feature row per (tile, sample), so hidden_0 is per sample
-        if (!fused) return bq_fail(ctx, BQ_ERR_ARG, "dropout site 0 needs the fused head");
-        KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * kFeatures + 2.0 * nb * T * kFeatures);
-        bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (kFeatures / 4)), 256, 0, ctx->stream>>>(
-            (const bf16*)m->feat_bf16.p, (bf16*)m->a0.p, nb, T, kFeatures, seed, tile_base, 0, thresh, masks_dev, m->n_sites,
-            m->slot[0], m->mask_w);
-        BQ_LAUNCH_CHECK(ctx);
-        g.M = nb * T;
-        g.out_row_off = h1_off * T;
-      } else {
-        g.M = nb;
-        g.out_row_off = h1_off;
-      }
-    } else {
-      if (fused) break;
-      // dropout site i: masked copy of the previous activation, one row per (tile, sample)
-      const bf16* src = (const bf16*)m->h_act[(i - 1) & 1].p;
-      const int per_sample = i >= 2;     // layer-1 input is per tile, deeper inputs are already per sample
-      if (per_sample) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers > 2 is not supported yet");
-      {
-        KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * Wd + 2.0 * nb * T * Wd);
-        bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (Wd / 4)), 256, 0, ctx->stream>>>(
-            src, (bf16*)m->a2.p, nb, T, Wd, seed, tile_base, i, thresh, masks_dev, m->n_sites, m->slot[i], m->mask_w);
-      }
+    if (m->sites & 1) {
+      // dropout on the pooled features: one masked copy of the feature row per (tile, sample), so hidden_0 is per sample
+      KScope ks(m, BQ_K_MC_EXPAND, 0, 2.0 * nb * kFeatures + 2.0 * nb * T * kFeatures);
+      bq::mc_expand_kernel<<<grid1d((int64_t)nb * T * (kFeatures / 4)), 256, 0, ctx->stream>>>(
+          (const bf16*)m->feat_bf16.p, (bf16*)m->a0.p, nb, T, kFeatures, seed, tile_base, 0, thresh, masks_dev, m->n_sites,
+          m->slot[0], m->mask_w);
       BQ_LAUNCH_CHECK(ctx);
       g.M = nb * T;
+      g.out_row_off = h1_off * T;
+    } else {
+      g.M = nb;
+      g.out_row_off = h1_off;
     }
     KScope ks(m, BQ_K_HEAD_GEMM, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
     if ((rc = launch_gemm(m, g, hg.ta, hg.tb, hg.tc, hg.tc, 64, &hg.tb2))) return rc;
   }
-  if (fused && n_head < 0) n_head = nb;
-  if (fused && n_head == 0) return BQ_OK;
-  if (fused) {
-    nb = n_head;
-    // ONE kernel: Philox masks -> hidden_1 (tcgen05) -> bias/ReLU -> mask -> prelogits -> softmax -> mean/std over T
-    bq::head::HeadParams hp;
-    hp.h1 = (const bf16*)m->h_act[0].p;
-    hp.b2 = (const float*)m->hidden[1]->shift.p;
-    hp.w3 = (const float*)m->w3.p;
-    hp.b3 = (const float*)m->b3.p;
-    hp.mean = (float*)m->out_mean.p;
-    hp.stdv = (float*)m->out_std.p;
-    hp.masks = masks_dev;
-    hp.n = nb; hp.T = T; hp.W = Wd; hp.C = NC;
-    hp.n_sites = m->n_sites; hp.slot1 = m->slot[1]; hp.slot2 = m->slot[2];
-    hp.mask_w = m->mask_w;
-    hp.h1_per_sample = (m->sites & 1) ? 1 : 0;
-    hp.inv_keep = 1.0f / (1.0f - m->cfg.dropout);
-    hp.inv_keep1 = (m->sites & 2) ? hp.inv_keep : 1.0f;
-    hp.inv_keep2 = (m->sites & 4) ? hp.inv_keep : 1.0f;
-    hp.thresh = thresh;
-    hp.seed = seed; hp.tile_base = tile_base;
-    const int groups = (nb + 3) / 4;
-    const int grid = groups < ctx->num_sms ? groups : ctx->num_sms;
-    KScope ks(m, BQ_K_HEAD_FUSED, 2.0 * nb * T * Wd * (Wd + NC), 2.0 * nb * Wd + 2.0 * Wd * Wd + 8.0 * nb * NC);
-    bq::head::mc_head_fused_kernel<<<grid, bq::head::kHThreads, bq::head::HeadSmem::kTotal, ctx->stream>>>(
-        m->head_gemms[1].tb, hp);
-    BQ_LAUNCH_CHECK(ctx);
-    return BQ_OK;
-  }
-  if (m->sites != 6) return bq_fail(ctx, BQ_ERR_ARG, "the three-kernel debug head supports the default dropout placement only");
-  const bf16* last = (const bf16*)m->h_act[(Hn - 1) & 1].p;
-  const int Teff = Hn == 1 ? 1 : T;
-  if (Hn == 1) return bq_fail(ctx, BQ_ERR_ARG, "hidden_layers == 1 is not supported yet");
-  const float inv_keep = 1.0f / (1.0f - m->cfg.dropout);
-  KScope ks(m, BQ_K_HEAD_FINAL, 2.0 * nb * T * Wd * NC, 2.0 * nb * T * Wd + 8.0 * nb * NC);
-  bq::head_final_kernel<<<nb, 256, (size_t)T * NC * sizeof(float), ctx->stream>>>(
-      last, (const float*)m->w3.p, (const float*)m->b3.p, Teff, Wd, NC, inv_keep, 1, seed, tile_base, Hn, thresh,
-      masks_dev, Hn, Hn - 1, (float*)m->out_mean.p, (float*)m->out_std.p);
+  if (n_head < 0) n_head = nb;
+  if (n_head == 0) return BQ_OK;
+  nb = n_head;
+  // ---- ONE kernel: Philox masks -> hidden_1 (tcgen05) -> bias/ReLU -> mask -> prelogits -> softmax -> mean/std over T
+  bq::head::HeadParams hp;
+  hp.h1 = (const bf16*)m->h_act[0].p;
+  hp.b2 = (const float*)m->hidden[1]->shift.p;
+  hp.w3 = (const float*)m->w3.p;
+  hp.b3 = (const float*)m->b3.p;
+  hp.mean = (float*)m->out_mean.p;
+  hp.stdv = (float*)m->out_std.p;
+  hp.masks = masks_dev;
+  hp.n = nb; hp.T = T; hp.W = Wd; hp.C = NC;
+  hp.n_sites = m->n_sites; hp.slot1 = m->slot[1]; hp.slot2 = m->slot[2];
+  hp.mask_w = m->mask_w;
+  hp.h1_per_sample = (m->sites & 1) ? 1 : 0;
+  hp.inv_keep = 1.0f / (1.0f - m->cfg.dropout);
+  hp.inv_keep1 = (m->sites & 2) ? hp.inv_keep : 1.0f;
+  hp.inv_keep2 = (m->sites & 4) ? hp.inv_keep : 1.0f;
+  hp.thresh = thresh;
+  hp.seed = seed; hp.tile_base = tile_base;
+  const int groups = (nb + 3) / 4;
+  const int grid = groups < ctx->num_sms ? groups : ctx->num_sms;
+  KScope ks(m, BQ_K_HEAD_FUSED, 2.0 * nb * T * Wd * (Wd + NC), 2.0 * nb * Wd + 2.0 * Wd * Wd + 8.0 * nb * NC);
+  bq::head::mc_head_fused_kernel<<<grid, bq::head::kHThreads, bq::head::HeadSmem::kTotal, ctx->stream>>>(m->head_gemms[1].tb, hp);
   BQ_LAUNCH_CHECK(ctx);
   return BQ_OK;
 }
@@ -1019,65 +887,34 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   m->n_sites = 0;
   for (int i = 0; i < 3; ++i) m->slot[i] = (m->sites >> i) & 1 ? m->n_sites++ : -1;
   m->mask_w = (m->sites & 1) ? kFeatures : cfg->hidden_width;
+  // Debug switches (never the default; each is exercised by a test): BQ_GEMM=simt runs every GEMM-shaped op on a plain
+  // CUDA-core kernel, BQ_GRAPH=off launches the backbone op by op, BQ_SEPMID=off runs the 728-wide middle flow as
+  // stand-alone depthwise + pointwise-GEMM kernels instead of the fused kernel.
   const char* g = getenv("BQ_GEMM");
-  m->use_simt = g && strcmp(g, "simt") == 0;   // debug switch: SIMT GEMM instead of tcgen05 (never the default)
-  m->gemm_direct_epi = g && strcmp(g, "direct") == 0;   // debug switch: per-thread global stores in the epilogue
-  m->gemm_2cta = !(g && (strcmp(g, "1cta") == 0 || strcmp(g, "direct") == 0));   // default: cta_group::2 pairs
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan2<bq::sm100::k2Stages>::kTotal);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages + 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan2<bq::sm100::k2Stages + 1>::kTotalNoRes);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_2cta_kernel<bq::sm100::k2Stages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan2<bq::sm100::k2Stages, true>::kTotalNoRes);
-  const char* gw = getenv("BQ_GEMM_WIDE");
-  m->gemm_wide = gw && strcmp(gw, "on") == 0;
-  const char* hv = getenv("BQ_HEAD");
-  m->head_fused = !(hv && strcmp(hv, "unfused") == 0) &&   // debug switch: three-kernel head (expand / GEMM / final)
-                  cfg->hidden_layers == 2 && cfg->hidden_width <= bq::head::kHMaxW;
-  cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::head::HeadSmem::kTotal);
-  const char* s2d = getenv("BQ_SEP2D");
-  m->sep2d = !(s2d && strcmp(s2d, "off") == 0);
-  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
-  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
-  const char* cc32 = getenv("BQ_DW_CC");
-  m->dw_cc32 = cc32 && atoi(cc32) == 32;
+  m->use_simt = g && strcmp(g, "simt") == 0;
   const char* gr = getenv("BQ_GRAPH");
   m->use_graph = !(gr && strcmp(gr, "off") == 0);
-  const char* sf = getenv("BQ_SEPCONV");
-  m->sep_fused = sf && strcmp(sf, "fused") == 0;
   const char* smid = getenv("BQ_SEPMID");
-  m->sep_mid = !(smid && strcmp(smid, "off") == 0) && !m->sep_fused && !m->use_simt;
+  m->sep_mid = !(smid && strcmp(smid, "off") == 0) && !m->use_simt;
+  using namespace bq::sm100;
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<k2Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan2<k2Stages>::kTotal);
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<k2Stages + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan2<k2Stages + 1>::kTotalNoRes);
+  cudaFuncSetAttribute(conv3x3_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+  cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::head::HeadSmem::kTotal);
+  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
+  cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
   cudaFuncSetAttribute(bq::sepmid::sepconv_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepmid::kSmem);
   cudaFuncSetAttribute(bq::sepmid::sepconv_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepmid::kSmem);
-  cudaFuncSetAttribute(bq::sepf::sepconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sepf::kSmem);
-  const char* c2 = getenv("BQ_CONV2");
-  m->conv2_is = !(c2 && strcmp(c2, "taps") == 0);
-  cudaFuncSetAttribute(bq::sm100::conv3x3_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sm100::kC2Smem);
-  const char* eb = getenv("BQ_ENTRY_BATCH");
-  if (eb) m->entry_batch = atoi(eb);
-  const char* dwv = getenv("BQ_DW");
-  // default 3 = persistent TMA-pipelined kernel; v1 / v2 / tc are the earlier generations kept as experiment switches
-  m->dw_mode = !dwv ? 3 : strcmp(dwv, "v1") == 0 ? 0 : strcmp(dwv, "v2") == 0 ? 1 : strcmp(dwv, "tc") == 0 ? 2 : 3;
   cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
   cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
   cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
   cudaFuncSetAttribute(bq::dwp::depthwise3x3_pipe_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwp::kSmem);
-  cudaFuncSetAttribute(bq::dwtc::depthwise3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::dwtc::kSmem);
-  cudaFuncSetAttribute(bq::depthwise3x3_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::kDwHalo * bq::kDwHalo * 64 * (int)sizeof(bf16));
   for (auto& e : m->ev) cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->consumed[i], cudaEventDisableTiming);
   }
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan<64, true>::kTotal);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan<64, false>::kTotal);
-  cudaFuncSetAttribute(bq::sm100::gemm_tcgen05_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       bq::sm100::SmemPlan<32, false>::kTotal);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete m; return bq_fail(ctx, BQ_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   *out = m;
@@ -1124,27 +961,13 @@ int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n
     int r;
     if ((r = need(ctx, ti, name + "/depthwise_kernel", {3, 3, cin, 1}, &d))) return r;
     {
-      // depthwise weights are bf16 operands of the tensor-core kernel; the CUDA-core debug kernels use the same
-      // (bf16-rounded) values widened to fp32 so that every path computes the same function
+      // depthwise taps are rounded to bf16 (what a bf16 model stores) and held widened to fp32 for the FFMA2 producers
       std::vector<float> dwr((size_t)9 * cin);
       for (size_t i = 0; i < dwr.size(); ++i) {
         const uint32_t u = (uint32_t)f32_to_bf16_rne(d->data[i]) << 16;
         memcpy(&dwr[i], &u, 4);
       }
       if ((r = upload(ctx, s->dw, dwr.data(), dwr.size() * 4))) return r;
-    }
-    {
-      const int chunks = (cin + 63) / 64;
-      std::vector<uint16_t> bd((size_t)chunks * 36 * 256, 0);
-      for (int ch = 0; ch < chunks; ++ch)
-        for (int tp = 0; tp < 9; ++tp)
-          for (int cg = 0; cg < 4; ++cg)
-            for (int n = 0; n < 16; ++n) {
-              const int c = ch * 64 + cg * 16 + n;
-              if (c < cin)
-                bd[((size_t)ch * 36 + tp * 4 + cg) * 256 + bq::dwtc::bdiag_index(n, n)] = f32_to_bf16_rne(d->data[(size_t)tp * cin + c]);
-            }
-      if ((r = upload(ctx, s->bdiag, bd.data(), bd.size() * 2))) return r;
     }
     if ((r = load_conv_gemm(ctx, ti, name, "pointwise_kernel", 1, cin, cout, s->pw))) return r;
     m->sep[name] = std::move(s);
@@ -1195,8 +1018,25 @@ int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n
   return BQ_OK;
 }
 
+static int predict_impl(bq_model* m, const uint8_t* tiles, bool f32_input, int64_t n, int32_t T, uint64_t seed,
+                        uint64_t tile_index_base, const uint8_t* masks, float* mean, float* std, float* features);
+
 int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint64_t seed, uint64_t tile_index_base,
                   const uint8_t* masks, float* mean, float* std, float* features) {
+  return predict_impl(m, tiles, false, n, T, seed, tile_index_base, masks, mean, std, features);
+}
+
+int bq_predict_uq_standardized(bq_model* m, const float* tiles, int64_t n, int32_t T, uint64_t seed, uint64_t tile_index_base,
+                               const uint8_t* masks, float* mean, float* std, float* features) {
+  if (!m) return BQ_ERR_ARG;
+  m->input_f32 = true;
+  const int rc = predict_impl(m, (const uint8_t*)tiles, true, n, T, seed, tile_index_base, masks, mean, std, features);
+  m->input_f32 = false;
+  return rc;
+}
+
+static int predict_impl(bq_model* m, const uint8_t* tiles, bool f32_input, int64_t n, int32_t T, uint64_t seed,
+                        uint64_t tile_index_base, const uint8_t* masks, float* mean, float* std, float* features) {
   if (!m) return BQ_ERR_ARG;
   bq_ctx* ctx = m->ctx;
   if (!m->weights_loaded) return bq_fail(ctx, BQ_ERR_STATE, "bq_predict_uq: weights not loaded");
@@ -1204,7 +1044,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
     return bq_fail(ctx, BQ_ERR_ARG, "bq_predict_uq: bad argument");
   BQ_CUDA(ctx, cudaSetDevice(ctx->device));
   const int B = m->max_batch, NC = m->cfg.n_classes, Wd = m->cfg.hidden_width, Hn = m->cfg.hidden_layers;
-  const size_t tile_bytes = (size_t)m->px * m->px * 3;
+  const size_t tile_bytes = (size_t)m->px * m->px * 3 * (f32_input ? sizeof(float) : 1);
   const size_t mask_per_tile = (size_t)T * m->n_sites * m->mask_w;
   const bool masks_on_dev = masks && bq_is_device_ptr(masks);
   if (masks && !masks_on_dev) {
@@ -1219,7 +1059,11 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
   // Host tiles: double-buffered staging, the H2D copy of micro-batch i+1 runs on its own stream while the
   // backbone of micro-batch i computes.  Device tiles are read in place.
   const bool tiles_on_dev = bq_is_device_ptr(tiles);
-  uint8_t* stage[2] = {(uint8_t*)m->tiles_dev.p, (uint8_t*)m->tiles_dev2.p};
+  if (f32_input && !tiles_on_dev) {
+    const int64_t cap = n < B ? n : B;                      // the interface is usually called tile by tile (results.py:249-257)
+    for (auto& b : m->tiles_f32) { int rcf = bq_alloc(ctx, b, (size_t)cap * tile_bytes + 64); if (rcf) return rcf; }
+  }
+  uint8_t* stage[2] = {(uint8_t*)(f32_input ? m->tiles_f32[0].p : m->tiles_dev.p), (uint8_t*)(f32_input ? m->tiles_f32[1].p : m->tiles_dev2.p)};
   auto issue_copy = [&](int64_t i0c, int slot) -> int {
     const int nbc = (int)((n - i0c < B) ? (n - i0c) : B);
     BQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->consumed[slot], 0));   // previous reader of this slot done
@@ -1254,7 +1098,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
         mdev = (const uint8_t*)m->masks_dev.p;
       }
     }
-    if (m->norm_kind == BQ_NORM_REINHARD_FAST) {
+    if (m->norm_kind == BQ_NORM_REINHARD_FAST && !f32_input) {
       if ((rc = bq_stain_launch(ctx, m->tiles_src, nb, m->px, (const float*)m->norm_lut.p, (float*)m->norm_stats.p,
                                 m->norm_means, m->norm_stds, (uint8_t*)m->tiles_norm.p)))
         return rc;
@@ -1265,7 +1109,7 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
     if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
       return rc;
     const bool last = i0 + B >= n;
-    if (m->head_fused) {
+    {
       // hidden_0 now (per micro-batch); the dropout-bearing layers once enough tiles are queued to fill the SMs
       // (site 0 only: the per-sample feature masks of THIS micro-batch -- its global tile index and its slice of the masks)
       if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0,
@@ -1283,13 +1127,6 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
       } else if (m->profiling) {
         cudaEventRecord(m->ev[6], ctx->stream);
       }
-    } else {
-      if ((rc = run_head(m, nb, T, seed, tile_index_base + (uint64_t)i0, mdev))) return rc;
-      if (m->profiling) cudaEventRecord(m->ev[6], ctx->stream);
-      if ((rc = bq_from_device(ctx, mean + (size_t)i0 * NC, m->out_mean.p, (size_t)nb * NC * 4)) ||
-          (rc = bq_from_device(ctx, std + (size_t)i0 * NC, m->out_std.p, (size_t)nb * NC * 4)))
-        return rc;
-      head_start = i0 + nb;
     }
     kprofile_collect(m);
     if (m->profiling) {

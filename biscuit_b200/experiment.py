@@ -51,50 +51,61 @@ class Experiment:
         Returns ``(df, thresholds)``: one row per usable outer fold (id, n_slides, fold, uq, patient_auc,
         patient_uq_perc, slide_auc, slide_uq_perc) and the mean over outer folds of tile_uq / slide_uq /
         slide_pred (None when no outer fold was usable).  Outer folds whose inner models or validation
-        table are missing are skipped with a warning, as in the reference."""
-        if id is None:
-            id = label
+        table are missing are skipped with a warning, as in the reference.
+
+        Per outer fold the inner-fold tables are uploaded ONCE (`threshold.FoldSet`) and both detection passes run on the
+        resident tables -- the second pass (tile threshold fixed, slide thresholds searched) reuses each fold's tile stage
+        and slide factorisation and only re-runs the filter + slide reduction + slide ROCs; the outer fold's validation
+        table is likewise resident for the patient- and the slide-level `apply`."""
         project = self.train_project
+        index = utils.ProjectIndex(project)
         patients = project.dataset(verification=None).patients()
-        if threshold_params is None:
-            threshold_params = {"tile_pred": "detect", "slide_pred": "detect", "plot": False, "patients": patients}
-        all_tile_uq, all_slide_uq, all_slide_pred = [], [], []
-        rows = []
-        for k in range(1, outer_k + 1):
-            try:
-                dfs = utils.df_from_cv(project, f"{label}-k{k}", outcome=self.outcome, k=inner_k, y_true=y_true,
-                                       y_pred=y_pred, uncertainty=uncertainty)        # :946-954
-            except ModelNotFoundError:
-                log.warning(f"Could not find {label} k-fold {k}; skipping")            # :955-957
+        params = dict(threshold_params) if threshold_params is not None else \
+            {"tile_pred": "detect", "slide_pred": "detect", "plot": False, "patients": patients}
+        headers = dict(y_true=y_true, y_pred=y_pred, uncertainty=uncertainty)
+        found = {"tile_uq": [], "slide_uq": [], "slide_pred": []}
+        report = []
+        for fold in range(1, outer_k + 1):
+            outer = self._outer_fold(index, label, fold, inner_k, tile_filename, headers)
+            if outer is None:
+                log.warning(f"Could not find {label} k-fold {fold}; skipping")       # :955-957, :963-965
                 continue
-            val_path = join(utils.find_model(project, f"{label}", kfold=k, outcome=self.outcome), tile_filename)
-            if not exists(val_path):                                                   # :963-965
-                log.warning(f"Could not find {label} k-fold {k}; skipping")
-                continue
-            tile_uq = threshold.from_cv(dfs, tile_uq="detect", slide_uq=None, **threshold_params)["tile_uq"]   # :966-971
-            thresholds = threshold.from_cv(dfs, tile_uq=tile_uq, slide_uq="detect", **threshold_params)        # :972-977
-            all_tile_uq.append(tile_uq)
-            all_slide_uq.append(thresholds["slide_uq"])
-            all_slide_pred.append(thresholds["slide_pred"])
-            tile_pred_df = utils.read_tile_predictions(val_path)                       # :980-985
-            utils.rename_cols(tile_pred_df, self.outcome, y_true=y_true, y_pred=y_pred, uncertainty=uncertainty)
-
-            def uq_auc_by_level(level):                                                # :988-996
-                results, _ = threshold.apply(tile_pred_df, plot=False, patients=patients, level=level, **thresholds)
-                return results["auc"], results["percent_incl"]
-
-            pt_auc, pt_perc = uq_auc_by_level("patient")
-            slide_auc, slide_perc = uq_auc_by_level("slide")
-            model = utils.find_model(project, f"{label}", kfold=k, epoch=1, outcome=self.outcome)
-            m_slides = utils.slides_from_model_manifest(model, dataset=None)          # :1008
-            rows.append({"id": id, "n_slides": len(m_slides), "fold": k, "uq": "include", "patient_auc": pt_auc,
-                         "patient_uq_perc": pt_perc, "slide_auc": slide_auc, "slide_uq_perc": slide_perc})
+            inner_tables, val_path = outer
+            with threshold.FoldSet(inner_tables) as inner:
+                tile_uq = inner.from_cv(tile_uq="detect", slide_uq=None, **params)["tile_uq"]      # :966-971
+                cuts = inner.from_cv(tile_uq=tile_uq, slide_uq="detect", **params)                 # :972-977
+            for key in found:
+                found[key].append(tile_uq if key == "tile_uq" else cuts[key])
+            validation = utils.read_tile_predictions(val_path)                        # :980-985
+            utils.rename_cols(validation, self.outcome, **headers)
+            with threshold.ResidentTable(_with_level_columns(validation, patients)) as table:
+                per_level = {level: threshold.apply_resident(table, patients=patients, level=level, **cuts)[0]
+                             for level in ("patient", "slide")}                       # :988-1001
+            manifest = utils.slides_from_model_manifest(index.path(label, self.outcome, epoch=1, kfold=fold))   # :1003-1008
+            report.append({"id": label if id is None else id, "n_slides": len(manifest), "fold": fold, "uq": "include",
+                           "patient_auc": per_level["patient"]["auc"], "patient_uq_perc": per_level["patient"]["percent_incl"],
+                           "slide_auc": per_level["slide"]["auc"], "slide_uq_perc": per_level["slide"]["percent_incl"]})
         df = pd.DataFrame()
-        for row in rows:                                                               # same concat as :1009-1018
+        for row in report:                       # row-by-row outer concat: the dtypes pandas infers match the reference's (:1009-1018)
             df = pd.concat([df, pd.DataFrame([row])], axis=0, join="outer", ignore_index=True)
-        thresholds = {
-            "tile_uq": None if not all_tile_uq else mean(all_tile_uq),
-            "slide_uq": None if not all_slide_uq else mean(all_slide_uq),
-            "slide_pred": None if not all_slide_pred else mean(all_slide_pred),
-        }
-        return df, thresholds
+        return df, {key: (mean(vals) if vals else None) for key, vals in found.items()}          # :1021-1025
+
+    def _outer_fold(self, index, label, fold, inner_k, tile_filename, headers):
+        """-> (inner-fold tables, path of the outer fold's validation table), or None when a model / table is missing"""
+        try:
+            for k in range(1, inner_k + 1):
+                index.folder(f"{label}-k{fold}", self.outcome, k)
+            inner = [index.validation_table(f"{label}-k{fold}", self.outcome, k, headers=headers)
+                     for k in range(1, inner_k + 1)]
+            val_path = join(index.path(label, self.outcome, kfold=fold), tile_filename)
+        except ModelNotFoundError:
+            return None
+        return (inner, val_path) if exists(val_path) else None
+
+
+def _with_level_columns(table, patients):
+    """the reference's `apply` adds the `patient` column itself (threshold.py:285-286); doing it before the table goes
+    resident lets both levels share one upload"""
+    if patients:
+        table["patient"] = table["slide"].map(patients)
+    return table

@@ -197,6 +197,65 @@ def _open_table(df, ctx=None) -> _DeviceTable:
     return _DeviceTable(df["y_pred"].to_numpy(), unc, df["y_true"].to_numpy(), ctx=ctx)
 
 
+class ResidentTable:
+    """A tile-prediction table kept RESIDENT on the GPU across calls.
+
+    The reference re-derives everything from the DataFrame in every call: the nested-CV caller runs `detect` twice per
+    inner fold and `apply` twice per outer fold on the same tables (experiment.py:966-1001).  Here the table is
+    uploaded once (`bq_table`), and what does not depend on the thresholds being searched is computed once and kept:
+
+      * the tile stage (validation, optional tile-ROC detection of `tile_pred`, the error / correct / incorrect /
+        y_pred_bin columns added to the DataFrame, threshold.py:140-177) -- keyed by the `tile_pred` setting;
+      * the first-appearance factorisation of the slide / patient keys (threshold.py:190).
+
+    A later call with another tile-UQ threshold only re-runs the filter + reference-order slide reduction and the
+    slide-level stage.  `apply_resident` / `detect_resident` are the entry points; `apply` / `detect` are the same code on
+    a table that lives for one call.  The DataFrame is mutated exactly as the reference mutates it."""
+
+    def __init__(self, df, ctx=None):
+        _check_columns(df)
+        self.df = df
+        self.tab = _open_table(df, ctx=ctx)
+        self.ctx = self.tab.ctx
+        self._tile_done = {}
+        self._keys = {}
+
+    def close(self):
+        if self.tab is not None:
+            self.tab.close()
+            self.tab = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def dtype(self):
+        return self.tab.dtype
+
+    def tile_stage(self, tile_pred, patients):
+        """-> the tile prediction threshold in force (detected once per table when 'detect')."""
+        key = "detect" if _is_detect(tile_pred) else (type(tile_pred).__name__, float(tile_pred))
+        if key not in self._tile_done:
+            # a different numeric threshold rewrites the derived columns; the incorrect flags on the device follow
+            self._tile_done = {key: _tile_stage(self.tab, self.df, tile_pred, patients)}
+        elif patients is not None and "patient" not in self.df.columns:
+            self.df["patient"] = _map_slides(self.tab, self.df, patients)
+        return self._tile_done[key]
+
+    def keys(self, level):
+        """(codes, uniques) of df[level] in first-appearance order, factorised once per level"""
+        if level not in self._keys:
+            fact = getattr(self.tab, "slide_factorized", None) if level == "slide" else None
+            self._keys[level] = fact if fact is not None else _factorize(self.df[level])
+        return self._keys[level]
+
+    def groups(self, level, tile_uq_eff, pred_thresh):
+        return _group_stage(self.tab, self.df, level, tile_uq_eff, pred_thresh, factorized=self.keys(level))
+
+
 # ----------------------------------------------------------------------------------------
 # tile level
 # ----------------------------------------------------------------------------------------
@@ -371,28 +430,39 @@ def apply(df, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
     Returns:
         dict with auc, percent_incl, acc, sensitivity, specificity; DataFrame of the kept groups
         (original integer index labels).  ({...None}, None) if no group-level ROC is possible."""
+    if plot:
+        log.warning("plot=True ignored: plotting is outside the scope of biscuit_b200")
     assert keep in ("high_confidence", "low_confidence")             # :281
     assert not (level == "patient" and patients is None)             # :282
     log.debug(f"Applying tile UQ threshold of {tile_uq:.5f}")         # :284 (TypeError on None)
-    if plot:
-        log.warning("plot=True ignored: plotting is outside the scope of biscuit_b200")
     if patients:                                                      # :285-286
         df["patient"] = df["slide"].map(patients)
     df[level]                                                         # :287 KeyError parity
-    _check_columns(df)
-    with _open_table(df) as tab:
-        _tile_stage(tab, df, tile_pred, patients)                     # :290-294
-        fact = _factorize(df[level])
-        n_before = len(fact[1]) + int((fact[0] < 0).any())            # :295 (NaN counts as a key)
-        unc_dtype = tab.dtype
-        tile_uq_eff = _cmp_scalar(tile_uq, unc_dtype) if tile_uq else None   # :297-298
-        try:
-            s_df, _ = _group_stage(tab, df, level, tile_uq_eff, slide_pred, factorized=fact)  # :305
-        except errors.ROCFailedError:
-            log.error("Unable to process slide predictions")
-            return {k: None for k in _RESULT_KEYS}, None              # :310-317
-        ctx = tab.ctx
-    return _apply_group_level(ctx, s_df, slide_uq, slide_pred, keep, level, n_before)
+    with ResidentTable(df) as table:
+        return apply_resident(table, tile_uq, slide_uq, tile_pred=tile_pred, slide_pred=slide_pred, keep=keep,
+                              patients=patients, level=level)
+
+
+def apply_resident(table: ResidentTable, tile_uq, slide_uq, tile_pred=0.5, slide_pred=0.5, plot=False,
+                   keep="high_confidence", title=None, patients=None, level="slide"):
+    """`apply` on a table that is already resident on the GPU (see :class:`ResidentTable`): the tile stage and the key
+    factorisation are reused from earlier calls, only the filter + slide reduction + slide-level stage run."""
+    assert keep in ("high_confidence", "low_confidence")
+    assert not (level == "patient" and patients is None)
+    df = table.df
+    if patients and "patient" not in df.columns:
+        df["patient"] = df["slide"].map(patients)
+    df[level]
+    table.tile_stage(tile_pred, patients)                             # :290-294
+    codes, uniques = table.keys(level)
+    n_before = len(uniques) + int((codes < 0).any())                  # :295 (NaN counts as a key)
+    tile_uq_eff = _cmp_scalar(tile_uq, table.dtype) if tile_uq else None   # :297-298
+    try:
+        s_df, _ = table.groups(level, tile_uq_eff, slide_pred)        # :305
+    except errors.ROCFailedError:
+        log.error("Unable to process slide predictions")
+        return {k: None for k in _RESULT_KEYS}, None                  # :310-317
+    return _apply_group_level(table.ctx, s_df, slide_uq, slide_pred, keep, level, n_before)
 
 
 def _apply_group_level(ctx, s_df, slide_uq, slide_pred, keep, level, n_before):
@@ -630,37 +700,43 @@ def detect(df, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pr
     Each of tile_uq / slide_uq / tile_pred / slide_pred is 'detect' (Youden's J on the matching
     ROC) or a float to use as given.  Returns (dict of the four thresholds, slide-level AUROC), or
     (all-None dict, None) when predictions contain NaN or no slide-level ROC is possible."""
-    none4 = {k: None for k in _THRESH_KEYS}
     if plot:
         log.warning("plot=True ignored: plotting is outside the scope of biscuit_b200")
-    _check_columns(df)
-    with _open_table(df) as tab:
-        try:
-            found_tile_pred = _tile_stage(tab, df, tile_pred, patients)   # :398-402
-        except errors.PredsContainNaNError:
-            log.error("Tile-level predictions contain NaNs; unable to process.")
-            return none4, None                                        # :403-405
-        if _is_detect(tile_pred):                                     # :407-408
-            tile_pred = found_tile_pred
-        if isinstance(tile_uq, _FLOAT_TYPES):                         # :411-412
-            tile_uq_eff = _cmp_scalar(tile_uq, tab.dtype)
-        elif not _is_detect(tile_uq):                                 # :413-415
-            log.debug("Not performing tile-level uncertainty thresholding.")
-            tile_uq, tile_uq_eff = None, None
-        else:                                                         # :416-426
-            if getattr(tab, "n_unc_nonfinite", 0):                     # roc_curve -> assert_all_finite (uncaught at :419)
-                raise ValueError("Input contains NaN or infinity.")
-            r = tab.tile_roc(_ffi.SCORE_UNCERTAINTY, _ffi.LABEL_INCORRECT)
-            tile_uq = _youden_or_raise(r)
-            log.debug(f"Tile-level optimal UQ threshold: {tile_uq:.4f}")
-            tile_uq_eff = float(tile_uq)
-        try:
-            s_df, slide_pred = _group_stage(tab, df, "slide", tile_uq_eff, slide_pred)  # :433-438
-        except errors.ROCFailedError:
-            log.error("Unable to process slide predictions")
-            return none4, None                                        # :439-441
-        ctx = tab.ctx
-    slide_uq, auc = _detect_group_level(ctx, s_df, slide_uq, slide_pred)
+    with ResidentTable(df) as table:
+        return detect_resident(table, tile_uq=tile_uq, slide_uq=slide_uq, tile_pred=tile_pred, slide_pred=slide_pred,
+                               patients=patients)
+
+
+def detect_resident(table: ResidentTable, tile_uq="detect", slide_uq="detect", tile_pred="detect", slide_pred="detect",
+                    plot=False, patients=None):
+    """`detect` on a GPU-resident table (see :class:`ResidentTable`)."""
+    none4 = {k: None for k in _THRESH_KEYS}
+    tab = table.tab
+    try:
+        found_tile_pred = table.tile_stage(tile_pred, patients)       # :398-402
+    except errors.PredsContainNaNError:
+        log.error("Tile-level predictions contain NaNs; unable to process.")
+        return none4, None                                            # :403-405
+    if _is_detect(tile_pred):                                         # :407-408
+        tile_pred = found_tile_pred
+    if isinstance(tile_uq, _FLOAT_TYPES):                             # :411-412
+        tile_uq_eff = _cmp_scalar(tile_uq, tab.dtype)
+    elif not _is_detect(tile_uq):                                     # :413-415
+        log.debug("Not performing tile-level uncertainty thresholding.")
+        tile_uq, tile_uq_eff = None, None
+    else:                                                             # :416-426
+        if getattr(tab, "n_unc_nonfinite", 0):                         # roc_curve -> assert_all_finite (uncaught at :419)
+            raise ValueError("Input contains NaN or infinity.")
+        r = tab.tile_roc(_ffi.SCORE_UNCERTAINTY, _ffi.LABEL_INCORRECT)
+        tile_uq = _youden_or_raise(r)
+        log.debug(f"Tile-level optimal UQ threshold: {tile_uq:.4f}")
+        tile_uq_eff = float(tile_uq)
+    try:
+        s_df, slide_pred = table.groups("slide", tile_uq_eff, slide_pred)   # :433-438
+    except errors.ROCFailedError:
+        log.error("Unable to process slide predictions")
+        return none4, None                                            # :439-441
+    slide_uq, auc = _detect_group_level(table.ctx, s_df, slide_uq, slide_pred)
     return {"tile_uq": tile_uq, "slide_uq": slide_uq,
             "tile_pred": tile_pred, "slide_pred": slide_pred}, auc
 
@@ -699,7 +775,49 @@ def from_cv(dfs, **kwargs):
     return _from_cv(dfs, detect, kwargs)
 
 
-def _from_cv(dfs, detect_fn, kwargs, require_patient=True):
+class FoldSet:
+    """The tile tables of a set of cross-validation folds, uploaded once and kept resident on the GPU.
+
+    `from_cv` may then be called repeatedly -- the nested-CV caller detects the tile-level UQ threshold first and the
+    slide-level thresholds with that tile threshold fixed (reference experiment.py:966-977) -- and every call after the
+    first reuses each fold's tile stage and key factorisation (:class:`ResidentTable`)."""
+
+    def __init__(self, dfs, ctx=None):
+        self.tables = []
+        try:
+            for df in dfs:
+                missing = [c for c in _CV_COLUMNS if c not in df.columns]
+                if missing:
+                    raise ValueError(f"DataFrame missing columns, expected {_CV_COLUMNS}, got: "
+                                     f"{', '.join(df.columns.tolist())}")
+                self.tables.append(ResidentTable(df, ctx=ctx))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        for t in self.tables:
+            t.close()
+        self.tables = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self):
+        return len(self.tables)
+
+    def from_cv(self, **kwargs):
+        """same result as ``threshold.from_cv([t.df for t in tables], **kwargs)`` (reference threshold.py:478-557)"""
+        return _from_cv(self.tables, lambda t, **kw: detect_resident(t, **kw), kwargs, columns_of=lambda t: t.df.columns)
+
+
+_CV_COLUMNS = ("y_true", "y_pred", "uncertainty", "slide", "patient")
+
+
+def _from_cv(dfs, detect_fn, kwargs, require_patient=True, columns_of=lambda df: df.columns):
     required = ("y_true", "y_pred", "uncertainty", "slide", "patient") if require_patient else \
                ("y_true", "y_pred", "uncertainty", "slide")
     skip_tile = "tile_uq_thresh" in kwargs and kwargs["tile_uq_thresh"] is None     # :513-516
@@ -707,9 +825,9 @@ def _from_cv(dfs, detect_fn, kwargs, require_patient=True):
     k_tile, k_slide, k_tile_pred, k_slide_pred = [], [], [], []
     for idx, df in enumerate(dfs):
         log.debug(f"Detecting thresholds from fold {idx}")
-        if not all(col in df.columns for col in required):            # :520-524
+        if not all(col in columns_of(df) for col in required):        # :520-524
             raise ValueError(f"DataFrame missing columns, expected {required}, got: "
-                             f"{', '.join(df.columns.tolist())}")
+                             f"{', '.join(list(columns_of(df)))}")
         thresholds, _ = detect_fn(df, **kwargs)                       # :525
         if thresholds["tile_uq"] is None or thresholds["slide_uq"] is None:   # :526-528
             log.debug(f"Skipping CV #{idx}, unable to detect threshold")

@@ -66,6 +66,7 @@ class UncertaintyInterface:
         self.ctx = ctx or _ffi.default_context(device)
         self.lib = self.ctx.lib
         self.num_uq = config.uq_samples
+        self.max_batch = int(max_batch)
         self.wsi_normalizer = None     # attribute the reference call site probes (results.py:251)
         cfg = _ffi.ModelConfig(tile_px=config.tile_px, hidden_width=config.hidden_layer_width,
                                hidden_layers=config.hidden_layers, n_classes=config.n_classes,
@@ -114,20 +115,28 @@ class UncertaintyInterface:
     # ------------------------------------------------------------------------------------
     def predict(self, tiles, T: int | None = None, seed: int = 0, tile_index_base: int = 0,
                 masks=None, return_features: bool = False, out_mean=None, out_std=None):
-        """tiles: uint8 NHWC [n, 299, 299, 3] (numpy, or a CUDA torch tensor used in place).
+        """tiles: NHWC [n, 299, 299, 3] -- uint8 raw RGB (decode + per-image standardisation fused into the first
+        convolution), or float32 ALREADY passed through `tf.image.per_image_standardization` as the reference's call site
+        does (results.py:255-257); numpy, or a CUDA torch tensor used in place.
         Returns (mean [n, C], std [n, C]) float32 -- population std over T dropout samples."""
         T = int(T or self.num_uq)
         n = int(tiles.shape[0])
         px = self.config.tile_px
         if tuple(tiles.shape[1:]) != (px, px, 3):
-            raise ValueError(f"tiles must be [n, {px}, {px}, 3] uint8, got {tuple(tiles.shape)}")
+            raise ValueError(f"tiles must be [n, {px}, {px}, 3], got {tuple(tiles.shape)}")
+        dt = str(tiles.dtype).replace("torch.", "")
+        if dt not in ("uint8", "float32"):
+            raise TypeError("tiles must be uint8 (raw RGB) or float32 (already per-image standardised), got " + dt)
         if isinstance(tiles, np.ndarray):
-            if tiles.dtype != np.uint8:
-                raise TypeError("tiles must be uint8 (raw RGB; standardisation happens on the GPU)")
             tiles = np.ascontiguousarray(tiles)
+        elif hasattr(tiles, "is_contiguous") and not tiles.is_contiguous():
+            raise ValueError("tiles must be contiguous (NHWC)")
         nc = self.config.n_classes
         mean = out_mean if out_mean is not None else np.empty((n, nc), np.float32)
         std = out_std if out_std is not None else np.empty((n, nc), np.float32)
+        for name, buf in (("out_mean", mean), ("out_std", std)):    # raw pointers cross the ABI: check them here
+            if not isinstance(buf, np.ndarray) or buf.dtype != np.float32 or buf.shape != (n, nc) or not buf.flags.c_contiguous:
+                raise ValueError(f"{name} must be a C-contiguous float32 array of shape {(n, nc)}")
         feats = np.empty((n, FEATURES), np.float32) if return_features else None
         if masks is not None:
             sites = self.config.dropout_sites
@@ -137,19 +146,20 @@ class UncertaintyInterface:
                 raise ValueError(f"masks must have shape {want}")
             if isinstance(masks, np.ndarray):
                 masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        entry = self.lib.bq_predict_uq if dt == "uint8" else self.lib.bq_predict_uq_standardized
         _ffi.check(self.ctx.handle,
-                   self.lib.bq_predict_uq(self.h, _ffi.ptr(tiles), n, T, C.c_uint64(seed),
-                                          C.c_uint64(tile_index_base), _ffi.ptr(masks), _ffi.ptr(mean),
-                                          _ffi.ptr(std), _ffi.ptr(feats)), "bq_predict_uq")
+                   entry(self.h, _ffi.ptr(tiles), n, T, C.c_uint64(seed), C.c_uint64(tile_index_base), _ffi.ptr(masks),
+                         _ffi.ptr(mean), _ffi.ptr(std), _ffi.ptr(feats)), "bq_predict_uq")
         if return_features:
             return mean, std, feats
         return mean, std
 
     def __call__(self, tiles, **kw):
-        """`logits, uncertainty = interface(batch)` (results.py:257): mean softmax [B, C] and the
-        class-1 std as [B, 1] -- for two classes both stds are equal up to rounding."""
-        mean, std = self.predict(tiles, **kw)
-        return mean, std[:, 1:2].copy()
+        """`logits, uncertainty = interface(batch)` (results.py:257): mean softmax [B, C] and the per-class std
+        [B, C] over the dropout samples, so the reference's `uncertainty[0][0]` (results.py:258) reads the class-0 std --
+        for two classes both stds agree up to rounding.  `batch` may be the standardised float32 batch the reference
+        passes, or raw uint8 tiles."""
+        return self.predict(tiles, **kw)
 
     # ------------------------------------------------------------------------------------
     def debug_stage(self, tiles: np.ndarray, stage: str) -> np.ndarray:

@@ -82,74 +82,113 @@ def auc(y_true, y_pred):
 
 
 # --- prediction-table loaders and model lookup --------------------------------
+#
+# Slideflow lays a project out as  models_dir/<5-digit id>-<outcome>-<label>-HP0[-kfold<k>]/  with the saved epoch in a
+# sub-folder of the same name + "_epoch<e>" and the tile predictions of the validation set next to it
+# (`tile_predictions_val_epoch1.csv | .parquet.gzip`).  The reference lists the directory again for every lookup
+# (utils.py:233-272 is called 2-3 times per fold); here the directory is indexed ONCE per project object and every lookup
+# is a dictionary access.  Names, precedence (csv before parquet) and exceptions are the reference's.
+
+_VAL_TABLE = "tile_predictions_val_epoch1"
+
+
+class ProjectIndex:
+    """name -> folder index of one Slideflow project's ``models_dir`` (built by a single directory listing)."""
+
+    def __init__(self, project):
+        self.root = project.models_dir
+        self.by_name = {}
+        for entry in os.listdir(self.root):
+            self.by_name.setdefault(entry[6:], []).append(entry)       # strip the '00042-' run id
+        self._patients = None
+        self._project = project
+
+    @staticmethod
+    def model_name(label, outcome, kfold=None):
+        return f"{outcome}-{label}-HP0" + ("" if kfold is None else f"-kfold{kfold}")
+
+    def folder(self, label, outcome, kfold=None):
+        name = self.model_name(label, outcome, kfold)
+        hits = self.by_name.get(name, ())
+        if len(hits) > 1:
+            raise MultipleModelsFoundError(f"Multiple matching models found matching {name}")
+        if not hits:
+            raise ModelNotFoundError(f"No matching model found matching {name}.")
+        return join(self.root, hits[0])
+
+    def path(self, label, outcome, epoch=None, kfold=None):
+        """the run folder, or the saved model of `epoch` inside it"""
+        run = self.folder(label, outcome, kfold)
+        return run if epoch is None else join(run, f"{self.model_name(label, outcome, kfold)}_epoch{epoch}")
+
+    def patients(self):
+        if self._patients is None:
+            self._patients = self._project.dataset().patients()
+        return self._patients
+
+    def validation_table(self, label, outcome, kfold, epoch=None, headers=None):
+        """tile predictions of one fold's validation set with the canonical column names and a `patient` column"""
+        where = self.path(label, outcome, epoch=epoch, kfold=kfold)
+        base = where if epoch is None else os.path.dirname(os.path.normpath(where))
+        for suffix, reader in ((".csv", pd.read_csv), (".parquet.gzip", pd.read_parquet)):
+            candidate = join(base, _VAL_TABLE + suffix)
+            if os.path.exists(candidate):
+                table = reader(candidate)
+                break
+        else:
+            raise OSError(f"Could not find tile predictions file at {where}")
+        rename_cols(table, outcome, **(headers or {}))
+        if "patient" not in table.columns:
+            table["patient"] = table["slide"].map(self.patients())
+        return table
+
+
+def _index(project) -> ProjectIndex:
+    return ProjectIndex(project)
+
 
 def find_model(project, label, outcome, epoch=None, kfold=None):
-    """Path of the trained model `{outcome}-{label}-HP0[-kfold{k}]` inside ``project.models_dir``
-    (Slideflow prefixes every model folder with a 5-digit id and a dash, hence the ``[6:]``);
-    with ``epoch`` the saved-model sub-folder, else the parent folder.  Raises
-    ModelNotFoundError / MultipleModelsFoundError (reference utils.py:233-272)."""
-    tail = "" if kfold is None else f"-kfold{kfold}"
-    name = f"{outcome}-{label}-HP0{tail}"
-    matching = [o for o in os.listdir(project.models_dir) if o[6:] == name]
-    if len(matching) > 1:
-        raise MultipleModelsFoundError(f"Multiple matching models found matching {name}")
-    if not matching:
-        raise ModelNotFoundError(f"No matching model found matching {name}.")
-    if epoch is not None:
-        return join(project.models_dir, matching[0], f"{name}_epoch{epoch}")
-    return join(project.models_dir, matching[0])
+    """Path of the trained model `{outcome}-{label}-HP0[-kfold{k}]` inside ``project.models_dir``; with ``epoch`` the
+    saved-model sub-folder, else the run folder.  ModelNotFoundError / MultipleModelsFoundError as the reference
+    (utils.py:233-272)."""
+    return _index(project).path(label, outcome, epoch=epoch, kfold=kfold)
 
 
 def model_exists(project, label, outcome, epoch=None, kfold=None):
-    """True if :func:`find_model` finds exactly one match (reference utils.py:275-292; more than
-    one match still raises, as there)."""
+    """Whether exactly one such model exists; several matches still raise (reference utils.py:275-292)."""
     try:
-        find_model(project, label, outcome, kfold=kfold, epoch=epoch)
-        return True
+        _index(project).folder(label, outcome, kfold)
     except ModelNotFoundError:
         return False
+    return True
 
 
 def find_cv(project, label, outcome, epoch=None, k=3):
     """Paths of the k cross-validation models of one experiment (reference utils.py:295-311)."""
-    return [find_model(project, label, outcome, epoch=epoch, kfold=_k) for _k in range(1, k + 1)]
+    index = _index(project)
+    return [index.path(label, outcome, epoch=epoch, kfold=fold) for fold in range(1, k + 1)]
 
 
 def read_tile_predictions(path):
     """One Slideflow tile-prediction table: ``.csv`` (slide column forced to str, reference
     experiment.py:980-981) or ``.parquet`` / ``.parquet.gzip`` (982-983); anything else is an
     OSError (984-985)."""
-    ext = path.rsplit(".", 1)[-1].lower()
-    if ext == "csv":
-        return pd.read_csv(path, dtype={"slide": str})
-    if ext in ("parquet", "gzip"):
-        return pd.read_parquet(path)
-    raise OSError(f"Unrecognized prediction filetype {path}")
+    kind = path.rsplit(".", 1)[-1].lower()
+    readers = {"csv": lambda f: pd.read_csv(f, dtype={"slide": str}), "parquet": pd.read_parquet, "gzip": pd.read_parquet}
+    if kind not in readers:
+        raise OSError(f"Unrecognized prediction filetype {path}")
+    return readers[kind](path)
 
 
 def df_from_cv(project, label, outcome, epoch=None, k=3, y_true=None, y_pred=None, uncertainty=None):
-    """Tile-prediction tables of the k cross-validation folds of `label`, columns renamed to
-    y_true / y_pred / uncertainty and a ``patient`` column added from the project's slide ->
-    patient map when the file has none (reference utils.py:190-228).  CSV wins over
-    ``.parquet.gzip`` when both exist, as in the reference."""
-    dfs = []
-    folders = find_cv(project, label, epoch=epoch, k=k, outcome=outcome)
-    patients = project.dataset().patients()
-    e = "" if epoch is None else "../"
-    for folder in folders:
-        csv_path = join(folder, f"{e}tile_predictions_val_epoch1.csv")
-        parquet_path = join(folder, f"{e}tile_predictions_val_epoch1.parquet.gzip")
-        if os.path.exists(csv_path):
-            df = pd.read_csv(csv_path)
-        elif os.path.exists(parquet_path):
-            df = pd.read_parquet(parquet_path)
-        else:
-            raise OSError(f"Could not find tile predictions file at {folder}")
-        rename_cols(df, outcome, y_true=y_true, y_pred=y_pred, uncertainty=uncertainty)
-        if "patient" not in df.columns:
-            df["patient"] = df["slide"].map(patients)
-        dfs.append(df)
-    return dfs
+    """The k validation tables of cross-validated experiment `label`, ready for `threshold.from_cv`: columns renamed
+    to y_true / y_pred / uncertainty, `patient` filled from the project's slide -> patient map when the file has none;
+    a float64 table when it came from CSV, float32 from parquet (reference utils.py:190-228)."""
+    index = _index(project)
+    for fold in range(1, k + 1):
+        index.folder(label, outcome, fold)                              # every fold is looked up before any file is read
+    headers = dict(y_true=y_true, y_pred=y_pred, uncertainty=uncertainty)
+    return [index.validation_table(label, outcome, fold, epoch=epoch, headers=headers) for fold in range(1, k + 1)]
 
 
 def slides_from_model_manifest(model_path, dataset=None):
@@ -169,62 +208,66 @@ def slides_from_model_manifest(model_path, dataset=None):
 
 # --- evaluation metrics ------------------------------------------------------
 
-def prediction_metrics(y_true, y_pred, threshold):
-    """AUC confidence interval (DeLong), accuracy, sensitivity / specificity and Youden's J with its
-    bootstrap confidence interval (reference utils.py:400-464).
+_N_BOOTSTRAP, _BOOTSTRAP_ROWS, _ALPHA = 500, 150, 0.05            # reference utils.py:420,430-431
 
-    The 500 bootstrap samples of 150 rows are drawn with the same ``np.random.choice`` calls as the
-    reference (so a seeded ``np.random`` gives the reference's numbers); their confusion matrices and the
-    DeLong placement values are computed on the GPU, the order-sensitive finish (``statistics.mean`` /
-    ``variance``, ``np.cov``, ``scipy.stats.norm``) by the same library calls as the reference."""
+
+def _confusion(labels, calls):
+    """(tp, fp, tn, fn) of boolean labels / calls as numpy integers"""
+    cell = np.bincount(2 * labels.astype(np.int64) + calls.astype(np.int64), minlength=4)
+    return cell[3], cell[1], cell[0], cell[2]
+
+
+def _bootstrap_confusions(labels, calls, draws):
+    """confusion counts [n_boot, 4] = (tp, fp, tn, fn) of every bootstrap resample, on the GPU (bq_bootstrap_confusion)"""
     import ctypes as C
+
+    from . import _ffi
+    ctx = _ffi.default_context()
+    n_boot, n_rows = draws.shape
+    counts = np.empty((n_boot, 4), np.int64)
+    lab8, call8 = np.ascontiguousarray(labels, dtype=np.uint8), np.ascontiguousarray(calls, dtype=np.uint8)
+    draws = np.ascontiguousarray(draws, dtype=np.int64)
+    _ffi.check(ctx.handle, ctx.lib.bq_bootstrap_confusion(ctx.handle, _ffi.ptr(lab8), _ffi.ptr(call8), int(labels.shape[0]),
+                                                          _ffi.ptr(draws), C.c_int32(n_boot), C.c_int32(n_rows),
+                                                          _ffi.ptr(counts)), "bq_bootstrap_confusion")
+    return counts
+
+
+def prediction_metrics(y_true, y_pred, threshold):
+    """AUC confidence interval (DeLong), accuracy, sensitivity / specificity and Youden's J with its bootstrap confidence
+    interval (reference utils.py:400-464).
+
+    The 500 x 150 bootstrap row draws come from ONE ``np.random.choice`` call -- the legacy generator fills it element by
+    element, so a seeded ``np.random`` yields exactly the rows of the reference's 500 consecutive calls -- and all 500
+    confusion matrices are counted by one kernel launch; the DeLong placement values are computed on the GPU as well.
+    The order-sensitive floating-point finish (``statistics.mean`` / ``variance`` over the per-resample Wilson-adjusted J,
+    ``np.cov``, ``scipy.stats.norm``) uses the library calls the reference uses, in its order: bit-identical results."""
     from statistics import mean, variance
 
     from scipy import stats
 
-    from . import _ffi
     from .delong import delong_roc_variance
 
-    yt = y_true.astype(bool)
-    yp = y_pred > threshold
-    alpha = 0.05
-    z = stats.norm.ppf((1 - alpha / 2))
-    tp = np.logical_and(yt, yp).sum()
-    fp = np.logical_and(np.logical_not(yt), yp).sum()
-    tn = np.logical_and(np.logical_not(yt), np.logical_not(yp)).sum()
-    fn = np.logical_and(yt, np.logical_not(yp)).sum()
-    acc = (tp + tn) / (tp + tn + fp + fn)
-    sensitivity = tp / (tp + fn)
-    specificity = tn / (tn + fp)
+    labels, calls = y_true.astype(bool), y_pred > threshold
+    z = stats.norm.ppf(1 - _ALPHA / 2)
+    tp, fp, tn, fn = _confusion(labels, calls)
+    sensitivity, specificity = tp / (tp + fn), tn / (tn + fp)
 
-    n_boot, n_samp = 500, 150                                         # utils.py:430-431
-    idx = np.empty((n_boot, n_samp), np.int64)
-    population = np.arange(yt.shape[0])
-    for b in range(n_boot):                                           # same RNG consumption as the reference
-        idx[b] = np.random.choice(population, size=(n_samp,))
-    ctx = _ffi.default_context()
-    counts = np.empty((n_boot, 4), np.int64)
-    yt8 = np.ascontiguousarray(yt, dtype=np.uint8)
-    yp8 = np.ascontiguousarray(yp, dtype=np.uint8)
-    _ffi.check(ctx.handle, ctx.lib.bq_bootstrap_confusion(ctx.handle, _ffi.ptr(yt8), _ffi.ptr(yp8), int(yt.shape[0]),
-                                                          _ffi.ptr(idx), C.c_int32(n_boot), C.c_int32(n_samp),
-                                                          _ffi.ptr(counts)), "bq_bootstrap_confusion")
-    _tp, _fp, _tn, _fn = counts[:, 0], counts[:, 1], counts[:, 2], counts[:, 3]
-    all_jac = (((_tn + 0.5 * z**2) / (_tn + _fp + z**2)) - ((_fn + 0.5 * z**2) / (_fn + _tp + z**2)))   # utils.py:438-439
-    all_jac = list(all_jac)
-    jac = mean(all_jac)
-    jac_var = variance(all_jac)
-    jac_low = jac - z * np.sqrt(jac_var)
-    jac_high = jac + z * np.sqrt(jac_var)
+    draws = np.random.choice(np.arange(labels.shape[0]), size=(_N_BOOTSTRAP, _BOOTSTRAP_ROWS))
+    b = _bootstrap_confusions(labels, calls, draws)
+    b_tp, b_fp, b_tn, b_fn = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    half = 0.5 * z**2                                                   # Wilson-type adjustment of both rates (:438-439)
+    j_boot = list(((b_tn + half) / (b_tn + b_fp + z**2)) - ((b_fn + half) / (b_fn + b_tp + z**2)))
+    j_mean, j_sd = mean(j_boot), np.sqrt(variance(j_boot))
 
-    if not np.array_equal(np.unique(y_true), [0, 1]):                 # utils.py:448-450
+    auc_low = auc_high = None
+    if np.array_equal(np.unique(y_true), [0, 1]):
+        auc, auc_var = delong_roc_variance(y_true, y_pred)
+        interval = stats.norm.ppf(np.abs(np.array([0, 1]) - _ALPHA / 2), loc=auc, scale=np.sqrt(auc_var))
+        interval[interval > 1] = 1
+        auc_low, auc_high = interval
+    else:                                                               # :448-450
         log.warning("Unable to calculate CI; NaNs exist")
-        ci = [None, None]
-    else:
-        delong_auc, auc_cov = delong_roc_variance(y_true, y_pred)
-        auc_std = np.sqrt(auc_cov)
-        lower_upper_q = np.abs(np.array([0, 1]) - alpha / 2)
-        ci = stats.norm.ppf(lower_upper_q, loc=delong_auc, scale=auc_std)
-        ci[ci > 1] = 1
-    return {"auc_low": ci[0], "auc_high": ci[1], "acc": acc, "sens": sensitivity, "spec": specificity,
-            "youden": sensitivity + specificity - 1, "youden_low": jac_low, "youden_high": jac_high}
+    return {"auc_low": auc_low, "auc_high": auc_high, "acc": (tp + tn) / (tp + tn + fp + fn), "sens": sensitivity,
+            "spec": specificity, "youden": sensitivity + specificity - 1,
+            "youden_low": j_mean - z * j_sd, "youden_high": j_mean + z * j_sd}

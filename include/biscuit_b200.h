@@ -170,6 +170,12 @@ int bq_predict_uq(bq_model* m, const uint8_t* tiles, int64_t n, int32_t T, uint6
                   uint64_t tile_index_base, const uint8_t* masks, float* mean, float* std,
                   float* features);
 
+/* The reference's LITERAL call (results.py:255-257): tiles already passed through tf.image.per_image_standardization,
+ * float32 NHWC [n, 299, 299, 3].  Same outputs; the tile statistics, the standardisation and the stain normaliser are
+ * skipped (the first convolution reads the floats as they are). */
+int bq_predict_uq_standardized(bq_model* m, const float* tiles, int64_t n, int32_t T, uint64_t seed,
+                               uint64_t tile_index_base, const uint8_t* masks, float* mean, float* std, float* features);
+
 /* Debug / parity hooks: run only the backbone, returning bf16-rounded activations of a named stage as
  * float32 (NHWC).  Used by tests to localise a mismatch; not part of the reference surface. */
 int bq_model_debug_stage(bq_model* m, const uint8_t* tiles, int64_t n, const char* stage, float* out,
@@ -191,6 +197,20 @@ enum {
 };
 int bq_model_kernel_profile(bq_model* m, double ms[BQ_PROFILE_KINDS], double flops[BQ_PROFILE_KINDS],
                             double bytes[BQ_PROFILE_KINDS], int64_t launches[BQ_PROFILE_KINDS]);
+
+/* ------------------------------------------------------------------------------------------------
+ * slide tile-grid heat map with uncertainty masking
+ *   replaces the array side of `hm = sf.Heatmap(slide, model)` + `hm.uncertainty[:, :, 0] > thresh` +
+ *   `hm.logits[uq_mask, :] = [-1, -1]` (results.py:216-227); tile extraction and rendering are Slideflow's.
+ * ---------------------------------------------------------------------------------------------- */
+/* logits / uncertainty [gy, gx, n_classes] float32: -1 everywhere, then cell (x, y) = grid_xy[t] of tile t receives
+ * mean[t] / stdv[t] (outputs of bq_predict_uq). */
+int bq_heatmap_build(bq_ctx* ctx, int64_t n, int32_t n_classes, const float* mean, const float* stdv, const int32_t* grid_xy,
+                     int32_t gx, int32_t gy, float* logits, float* uncertainty);
+/* mask[cell] = uncertainty[cell][0] > thresh (float64 compare; apply NumPy's scalar promotion to `thresh` first);
+ * logits of masked cells := -1 in place. */
+int bq_heatmap_mask(bq_ctx* ctx, int64_t cells, int32_t n_classes, const float* uncertainty, double thresh, float* logits,
+                    uint8_t* mask);
 
 /* ------------------------------------------------------------------------------------------------
  * multi-GPU exchange (one process -- or host thread -- per GPU)

@@ -35,6 +35,18 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)
+    # two-classifier DeLong test (reference delong.py:110-123)
+    from .metrics_oracle import DELONG_TEST_CASES, make_delong_test_case
+    dt = {"versions": out["versions"], "generator": "oracle/make_golden_metrics.py (reference delong.delong_roc_test, np.float restored)",
+          "cases": {}}
+    for name, kw in DELONG_TEST_CASES.items():
+        y, a, b = make_delong_test_case(kw)
+        with reference_with_np_float():
+            lp = R.delong.delong_roc_test(y, a, b)
+        dt["cases"][name] = {"kwargs": kw, "log10_p": enc(np.float64(lp[0, 0])), "shape": list(lp.shape)}
+        print(name, lp)
+    with open(OUT.replace("metrics_golden", "delong_test_golden"), "w") as f:
+        json.dump(dt, f, indent=1)
 
 
 if __name__ == "__main__":

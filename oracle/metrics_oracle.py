@@ -47,6 +47,38 @@ def delong_roc_variance(ground_truth, predictions):
     return aucs[0], np.cov(v01) / m + np.cov(v10) / n
 
 
+def delong_roc_test(ground_truth, predictions_one, predictions_two):
+    """log10 p-value of the two-classifier DeLong test (delong.py:76-86, 110-123): 1 x 1 array"""
+    assert np.array_equal(np.unique(ground_truth), [0, 1])
+    order = (-ground_truth).argsort()
+    m = int(ground_truth.sum())
+    p = np.vstack((predictions_one, predictions_two))[:, order]
+    n = p.shape[1] - m
+    tx = np.stack([midrank(p[r, :m]) for r in range(2)])
+    ty = np.stack([midrank(p[r, m:]) for r in range(2)])
+    tz = np.stack([midrank(p[r]) for r in range(2)])
+    aucs = tz[:, :m].sum(axis=1) / m / n - float(m + 1.0) / 2.0 / n
+    cov = np.cov((tz[:, :m] - tx) / n) / m + np.cov(1.0 - (tz[:, m:] - ty) / m) / n
+    lvec = np.array([[1, -1]])
+    z = np.abs(np.diff(aucs)) / np.sqrt(np.dot(np.dot(lvec, cov), lvec.T))
+    return np.log10(2) + stats.norm.logsf(z, loc=0, scale=1) / np.log(10)
+
+
+# seeded inputs of the DeLong-test golden (tests/golden/delong_test_golden.json, oracle/make_golden_metrics.py)
+DELONG_TEST_CASES = {"f32_400": dict(n=400, seed=11, dtype="float32"), "f64_900_ties": dict(n=900, seed=12, dtype="float64", ties=40),
+                     "f32_3000": dict(n=3000, seed=13, dtype="float32")}
+
+
+def make_delong_test_case(kw):
+    rng = np.random.default_rng(kw["seed"])
+    y = rng.integers(0, 2, kw["n"]).astype(np.int64)
+    a = np.clip(0.5 + 0.15 * (2 * y - 1) + rng.normal(0, 0.3, kw["n"]), 0, 1)
+    b = np.clip(0.5 + 0.08 * (2 * y - 1) + rng.normal(0, 0.3, kw["n"]), 0, 1)
+    if kw.get("ties"):
+        a, b = np.round(a * kw["ties"]) / kw["ties"], np.round(b * kw["ties"]) / kw["ties"]
+    return y, a.astype(kw["dtype"]), b.astype(kw["dtype"])
+
+
 def prediction_metrics(y_true, y_pred, threshold):
     yt = y_true.astype(bool)
     yp = y_pred > threshold

@@ -51,3 +51,12 @@ def test_live_reference_matches_oracle():
         for k in ref:
             assert same_scalar(np.float64(ref[k]), np.float64(mine[k])), (k, ref[k], mine[k])
         assert float(ref_dl[0]) == float(mine_dl[0]) and float(ref_dl[1]) == float(mine_dl[1])
+
+
+@pytest.mark.parametrize("name", sorted(MO.DELONG_TEST_CASES))
+def test_delong_test_oracle_matches_golden(name):
+    """two-classifier DeLong test (reference delong.py:110-123): the oracle restatement vs the reference's committed output"""
+    g = load_golden("delong_test_golden.json")["cases"][name]
+    y, a, b = MO.make_delong_test_case(MO.DELONG_TEST_CASES[name])
+    lp = MO.delong_roc_test(y, a, b)
+    assert list(lp.shape) == g["shape"] and same_scalar(np.float64(lp[0, 0]), dec(g["log10_p"])), (lp, dec(g["log10_p"]))

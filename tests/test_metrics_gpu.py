@@ -48,3 +48,14 @@ def test_errors():
     from biscuit_b200.delong import delong_roc_variance
     with pytest.raises(AssertionError):
         delong_roc_variance(np.ones(10, np.int64), np.linspace(0, 1, 10))
+
+
+@pytest.mark.parametrize("name", sorted(MO.DELONG_TEST_CASES))
+def test_delong_roc_test_matches_reference_golden(name):
+    """`delong_roc_test` (reference delong.py:110-123): placement values of both classifiers on the GPU, bit-exact log10 p"""
+    from biscuit_b200.delong import delong_roc_test
+    from helpers import dec, same_scalar
+    g = load_golden("delong_test_golden.json")["cases"][name]
+    y, a, b = MO.make_delong_test_case(MO.DELONG_TEST_CASES[name])
+    lp = delong_roc_test(y, a, b)
+    assert list(lp.shape) == g["shape"] and same_scalar(np.float64(lp[0, 0]), dec(g["log10_p"])), (lp, dec(g["log10_p"]))

@@ -139,7 +139,7 @@ def test_sample_sweep_and_call_surface(iface, tiles):
         if t == 1:
             assert (std == 0).all()
     logits, unc = iface(tiles[:2])                     # reference call surface (results.py:257)
-    assert logits.shape == (2, 2) and unc.shape == (2, 1)
+    assert logits.shape == (2, 2) and unc.shape == (2, 2)          # per-class std: the reference reads uncertainty[0][0]
 
 
 def test_device_resident_tiles(iface, tiles):
@@ -185,27 +185,6 @@ def test_fused_head_sample_chunks_vs_oracle(iface, tiles, oracle_bf16, t_samples
     assert np.array_equal(a[0], mean) and np.array_equal(a[1], std)      # Philox == injected masks
 
 
-def test_unfused_head_debug_path_agrees():
-    """BQ_HEAD=unfused (expand + GEMM + final kernels) vs the default single fused head kernel"""
-    code = (
-        "import numpy as np, sys\n"
-        "from oracle import synth\n"
-        "from biscuit_b200.weights import random_init\n"
-        "from biscuit_b200.uq import UncertaintyInterface\n"
-        "i = UncertaintyInterface(random_init(seed=1), max_batch=3)\n"
-        "m, s = i.predict(synth.tiles_u8(5, seed=0), T=30, seed=5)\n"
-        "np.save(sys.argv[1], np.concatenate([m.ravel(), s.ravel()]))\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for mode in ("unfused", "fused"):
-        path = f"/tmp/bq_head_{mode}.npy"
-        env = dict(os.environ, BQ_HEAD=mode, PYTHONPATH=root)
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
-        outs.append(np.load(path))
-    print("unfused vs fused head: max d", np.abs(outs[0] - outs[1]).max())
-    assert np.abs(outs[0] - outs[1]).max() <= 2e-4
-
-
 def test_repeatable_at_production_batch():
     """Same tiles, same seed, production micro-batch (256) and more tiles than one batch: every run must be
     BIT-identical (features, mean, std).  Guards the persistent kernels' smem pipelines: a parity-aliasing bug in the
@@ -229,29 +208,6 @@ def test_repeatable_at_production_batch():
     # the 50 distinct tiles repeat 14 times across different micro-batch positions / SMs: copies must agree exactly
     f = outs[0][2].reshape(n // 50, 50, -1)
     assert all(f[0].tobytes() == f[k].tobytes() for k in range(1, n // 50)), "copies of the same tile differ"
-
-
-def test_depthwise_generations_bit_identical():
-    """BQ_DW=v2 (one tile per block) and the default persistent pipelined kernel perform the same fp32 FMAs in the
-    same tap order, so the whole network output must be bit-identical between them (300 tiles at batch 128: covers
-    18- and 19-column tiles, 56- and 64-channel chunks, partially idle warps)."""
-    code = (
-        "import numpy as np, sys, torch\n"
-        "from oracle import synth\n"
-        "from biscuit_b200.weights import random_init\n"
-        "from biscuit_b200.uq import UncertaintyInterface\n"
-        "i = UncertaintyInterface(random_init(seed=1), max_batch=128)\n"
-        "t = torch.from_numpy(synth.tiles_u8(60, seed=4)).cuda().repeat(5, 1, 1, 1).contiguous()\n"
-        "m, s, f = i.predict(t, T=5, seed=5, return_features=True)\n"
-        "np.save(sys.argv[1], np.concatenate([m.ravel(), s.ravel(), f.ravel()]))\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for mode in ("v2", "pipe"):
-        path = f"/tmp/bq_dw_{mode}.npy"
-        env = dict(os.environ, BQ_DW=mode, PYTHONPATH=root)
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=600)
-        outs.append(np.load(path))
-    assert outs[0].tobytes() == outs[1].tobytes(), f"max |d| = {np.abs(outs[0] - outs[1]).max()}"
 
 
 def test_results_do_not_depend_on_micro_batch():
@@ -454,3 +410,23 @@ def test_dropout_sites_config_errors(weights):
             it.predict(np.zeros((1, 299, 299, 3), np.uint8), T=2, masks=np.ones((1, 2, 2, 1024), np.uint8))
     finally:
         it.close()
+
+
+def test_standardized_float_input_is_the_reference_call(iface, tiles, oracle_bf16):
+    """The reference's literal call site (results.py:249-258): `parsed = tf.image.per_image_standardization(tile)`,
+    `logits, uncertainty = interface(tf.expand_dims(parsed, 0))`, `uncertainty[0][0]`.  A float32 batch standardised by
+    the caller (here: the oracle's restatement of per_image_standardization) must give what the fused uint8 path gives, up
+    to the fp32 rounding of computing (x - mean) * (1 / std) on the host instead of in the kernel."""
+    o, _, _ = oracle_bf16
+    parsed = o.standardize(tiles[:3]).permute(0, 2, 3, 1).contiguous().numpy()          # float32 NHWC, standardised
+    assert parsed.dtype == np.float32 and abs(float(parsed[0].mean())) < 1e-3
+    m_f, s_f, f_f = iface.predict(parsed, T=T, seed=SEED, return_features=True)
+    m_u, s_u, f_u = iface.predict(tiles[:3], T=T, seed=SEED, return_features=True)
+    assert np.abs(f_f - f_u).max() <= 2e-2 * np.abs(f_u).max()
+    assert np.abs(m_f - m_u).max() <= 3e-3 and np.abs(s_f - s_u).max() <= 3e-3
+    logits, uncertainty = iface(parsed[:1], T=T, seed=SEED)
+    assert logits.shape == (1, 2) and float(uncertainty[0][0]) == float(s_f[0, 0])
+    with pytest.raises(TypeError):
+        iface.predict(tiles[:1].astype(np.int32))
+    with pytest.raises(ValueError):
+        iface.predict(tiles[:2], out_mean=np.empty((2, 2), np.float64))
