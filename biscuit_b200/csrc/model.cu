@@ -19,6 +19,7 @@
 #include "dwpipe_sm100.cuh"
 #include "sepconv2d_sm100.cuh"
 #include "sepmid_sm100.cuh"
+#include "conv1_sm100.cuh"
 #include "stain_sm100.cuh"
 
 int bq_stain_launch(bq_ctx* ctx, const uint8_t* tiles_dev, int64_t n, int32_t px, const float* lut_dev, float* stats_dev,
@@ -240,6 +241,7 @@ struct bq_model {
 
   // weights
   DevBuf conv1_w, conv1_scale, conv1_shift;    // fp32 [27][32], [32], [32]
+  DevBuf conv1_wtc, conv1_sumw;                // tensor-core form of the same filter: bf16 [96][32] (hi | mid | lo thirds of fp32), fp32 [32] tap sums
   PwWeights conv2;
   std::map<std::string, std::unique_ptr<SepWeights>> sep;
   std::map<std::string, std::unique_ptr<PwWeights>> res;
@@ -596,7 +598,17 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
     case OP_CONV1: {
       KScope ks(m, BQ_K_CONV1, 2.0 * nb * op.Ho * op.Ho * 27 * 32, (double)nb * px * px * 3 + act * nb * op.Ho * op.Ho * 32);
       dim3 grid((op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, (op.Ho + bq::kC1Tile - 1) / bq::kC1Tile, nb);
-      if (m->input_f32)
+      if (!m->input_f32 && !m->use_simt && px == bq::conv1tc::kIn) {
+        // raw uint8 pixels on the tensor cores, standardisation applied behind the convolution (conv1_sm100.cuh)
+        bq::conv1tc::Conv1Params cp;
+        cp.tiles = m->tiles_src; cp.mean = (const float*)m->mean.p; cp.inv_std = (const float*)m->inv_std.p;
+        cp.w = (const bf16*)m->conv1_wtc.p; cp.sumw = (const float*)m->conv1_sumw.p;
+        cp.scale = (const float*)m->conv1_scale.p; cp.shift = (const float*)m->conv1_shift.p;
+        cp.out = op.out; cp.n_img = nb;
+        const int items = nb * bq::conv1tc::kItemsPerImg;
+        const int g1 = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;
+        bq::conv1tc::conv1_tc_kernel<<<g1, bq::conv1tc::kThreads, bq::conv1tc::kSmem, ctx->stream>>>(cp);
+      } else if (m->input_f32)
         bq::conv1_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)m->tiles_src, (const float*)m->mean.p,
                                                               (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
                                                               (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
@@ -948,6 +960,31 @@ int bq_model_load_weights(bq_model* m, const bq_named_tensor* tensors, int32_t n
     const bq_named_tensor* k;
     if ((rc = need(ctx, ti, "block1_conv1/kernel", {3, 3, 3, 32}, &k))) return rc;
     if ((rc = upload(ctx, m->conv1_w, k->data, 27 * 32 * 4))) return rc;
+    {
+      // conv1_tc_kernel: w = hi + mid + lo with three bf16 terms (3 x 8 significand bits = fp32's 24, each residual is
+      // exact), rows = part * 32 + channel, K = tap * 3 + ci padded 27 -> 32; and the per-channel tap sum that carries
+      // the per-image mean through the convolution
+      std::vector<uint16_t> wt((size_t)96 * 32, 0);
+      std::vector<float> sumw(32);
+      for (int c = 0; c < 32; ++c) {
+        double acc = 0.0;
+        for (int kk = 0; kk < 27; ++kk) {
+          const float w = k->data[(size_t)kk * 32 + c];
+          acc += (double)w;
+          float rem = w;
+          for (int part = 0; part < 3; ++part) {
+            const uint16_t b = f32_to_bf16_rne(rem);
+            const uint32_t u = (uint32_t)b << 16;
+            float bf;
+            memcpy(&bf, &u, 4);
+            wt[(size_t)(part * 32 + c) * 32 + kk] = b;
+            rem -= bf;
+          }
+        }
+        sumw[c] = (float)acc;
+      }
+      if ((rc = upload(ctx, m->conv1_wtc, wt.data(), wt.size() * 2)) || (rc = upload(ctx, m->conv1_sumw, sumw.data(), 32 * 4))) return rc;
+    }
     PwWeights tmp;
     if ((rc = load_bn(ctx, ti, "block1_conv1_bn", 32, tmp))) return rc;
     m->conv1_scale.release(); m->conv1_shift.release();
