@@ -39,7 +39,9 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, float* __restrict__ mean,
-                  float* __restrict__ inv_std) {
+                  float* __restrict__ inv_std, const float* __restrict__ c1_sumw = nullptr,
+                  const float* __restrict__ c1_scale = nullptr, const float* __restrict__ c1_shift = nullptr,
+                  float* __restrict__ c1_affine = nullptr /*[n][64]: per-tile (g, h) of conv1_tc_kernel's epilogue*/) {
   const uint8_t* src = tiles + (int64_t)blockIdx.x * bytes_per_tile;
   unsigned long long s = 0, s2 = 0;
   // head up to 16-byte alignment, vector body, tail
@@ -72,6 +74,7 @@ tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, flo
     s2 += x * x;
   }
   __shared__ unsigned long long sh[2][16];
+  __shared__ double stat[2];
   for (int o = 16; o; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
@@ -90,6 +93,18 @@ tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, flo
     if (sd < floor_sd) sd = floor_sd;
     mean[blockIdx.x] = (float)m;
     inv_std[blockIdx.x] = (float)(1.0 / sd);
+    stat[0] = m; stat[1] = 1.0 / sd;
+  }
+  if (c1_affine) {
+    // block1_conv1 is bias-free and 'valid': BN(conv(W, (x - m) / sd)) = conv(W, x) * g + h with, per output channel,
+    // g = scale / sd and h = shift - m * sum(W) * g  (fp64 here, one fp32 FMA per output in the kernel)
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int c = threadIdx.x;
+      const double g = stat[1] * (double)c1_scale[c];
+      c1_affine[(int64_t)blockIdx.x * 64 + c] = (float)g;
+      c1_affine[(int64_t)blockIdx.x * 64 + 32 + c] = (float)((double)c1_shift[c] - stat[0] * (double)c1_sumw[c] * g);
+    }
   }
 }
 

@@ -242,6 +242,7 @@ struct bq_model {
   // weights
   DevBuf conv1_w, conv1_scale, conv1_shift;    // fp32 [27][32], [32], [32]
   DevBuf conv1_wtc, conv1_sumw;                // tensor-core form of the same filter: bf16 [96][32] (hi | mid | lo thirds of fp32), fp32 [32] tap sums
+  DevBuf conv1_affine;                         // fp32 [max_batch][64]: per-tile epilogue constants of conv1_tc_kernel (tile_stats_kernel)
   PwWeights conv2;
   std::map<std::string, std::unique_ptr<SepWeights>> sep;
   std::map<std::string, std::unique_ptr<PwWeights>> res;
@@ -414,7 +415,7 @@ int build_plan(bq_model* m) {
   int rc;
   if ((rc = bq_alloc(ctx, m->tiles_dev, (size_t)B * px * px * 3 + 64)) ||
       (rc = bq_alloc(ctx, m->tiles_dev2, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
-      (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
+      (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->conv1_affine, (size_t)B * 64 * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
       (rc = bq_alloc(ctx, m->feat_bf16, (size_t)B * kFeatures * 2)) ||
       (rc = bq_alloc(ctx, m->out_mean, (size_t)m->head_batch * m->cfg.n_classes * 4)) ||
       (rc = bq_alloc(ctx, m->out_std, (size_t)m->head_batch * m->cfg.n_classes * 4)))
@@ -427,7 +428,10 @@ int build_plan(bq_model* m) {
 
   // ---- block 1
   { Op op; op.kind = OP_STATS; op.stage = 0; m->plan.push_back(op); }
-  { Op op; op.kind = OP_CONV1; op.stage = 0; op.out = A.p(0); op.H = px; op.Ho = s1; op.tag = "block1_conv1"; m->plan.push_back(op); }
+  { Op op; op.kind = OP_CONV1; op.stage = 0; op.out = A.p(0); op.H = px; op.Ho = s1; op.tag = "block1_conv1";
+    // output of conv1_tc_kernel as a [tiles * 149 * 149, 32] matrix: one [32 pixels x 32 channels] box per epilogue warp
+    if ((rc = make_tmap(ctx, &op.tc, A.p(0), (uint64_t)B * s1 * s1, 32, 32, 32, 32))) return rc;
+    m->plan.push_back(op); }
   {
     Op op; op.kind = OP_GEMM; op.stage = 1; op.tag = "block1_conv2";
     op.rows_per_tile = s1 * s1; op.blk_k = 32;
@@ -592,7 +596,9 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       if (m->input_f32) return BQ_OK;              // standardised by the caller
       KScope ks(m, BQ_K_STATS, 0, (double)nb * px * px * 3);
       bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>(m->tiles_src, (int64_t)px * px * 3,
-                                                        (float*)m->mean.p, (float*)m->inv_std.p);
+                                                        (float*)m->mean.p, (float*)m->inv_std.p, (const float*)m->conv1_sumw.p,
+                                                        (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
+                                                        (float*)m->conv1_affine.p);
       break;
     }
     case OP_CONV1: {
@@ -601,13 +607,11 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       if (!m->input_f32 && !m->use_simt && px == bq::conv1tc::kIn) {
         // raw uint8 pixels on the tensor cores, standardisation applied behind the convolution (conv1_sm100.cuh)
         bq::conv1tc::Conv1Params cp;
-        cp.tiles = m->tiles_src; cp.mean = (const float*)m->mean.p; cp.inv_std = (const float*)m->inv_std.p;
-        cp.w = (const bf16*)m->conv1_wtc.p; cp.sumw = (const float*)m->conv1_sumw.p;
-        cp.scale = (const float*)m->conv1_scale.p; cp.shift = (const float*)m->conv1_shift.p;
-        cp.out = op.out; cp.n_img = nb;
+        cp.tiles = m->tiles_src; cp.affine = (const float*)m->conv1_affine.p;
+        cp.w = (const bf16*)m->conv1_wtc.p; cp.out = op.out; cp.n_img = nb;
         const int items = nb * bq::conv1tc::kItemsPerImg;
         const int g1 = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;
-        bq::conv1tc::conv1_tc_kernel<<<g1, bq::conv1tc::kThreads, bq::conv1tc::kSmem, ctx->stream>>>(cp);
+        bq::conv1tc::conv1_tc_kernel<<<g1, bq::conv1tc::kThreads, bq::conv1tc::kSmem, ctx->stream>>>(op.tc, cp);
       } else if (m->input_f32)
         bq::conv1_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)m->tiles_src, (const float*)m->mean.p,
                                                               (const float*)m->inv_std.p, (const float*)m->conv1_w.p,
@@ -912,6 +916,7 @@ int bq_model_create(bq_ctx* ctx, const bq_model_config* cfg, bq_model** out) {
   cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<k2Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan2<k2Stages>::kTotal);
   cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<k2Stages + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan2<k2Stages + 1>::kTotalNoRes);
   cudaFuncSetAttribute(conv3x3_is_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2Smem);
+  cudaFuncSetAttribute(bq::conv1tc::conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::conv1tc::kSmem);
   cudaFuncSetAttribute(bq::head::mc_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::head::HeadSmem::kTotal);
   cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
   cudaFuncSetAttribute(bq::sep2d::sepconv2d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bq::sep2d::smem_bytes(256));
