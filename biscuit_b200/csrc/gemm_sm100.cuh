@@ -196,6 +196,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t s
                ::"l"((uint64_t)tmap), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recent bulk store have finished reading their smem source (double-buffered staging)
@@ -524,7 +529,9 @@ constexpr int kC2WinRows = 512;                          // 4 boxes x 128 rows >
 constexpr int kC2WinBytes = kC2WinRows * 64;             // 32 KB
 constexpr int kC2BBytes = 9 * 64 * 64;                   // 36 KB: nine taps x [64 n][32 k] bf16
 constexpr int kC2AccStages = 4;
-constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + 256 + 1024;
+constexpr int kC2OutTile = 32 * 64;                      // one epilogue warp's staging tile: [32 px][32 ch] bf16, SWIZZLE_64B
+constexpr int kC2OutBytes = 8 * 2 * kC2OutTile;          // eight epilogue warps, double-buffered
+constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + kC2OutBytes + 256 + 1024;
 
 // warp 0 TMA, warps 1 and 6 MMA issue (small MMAs are issue-latency bound), warps 2-5 and 7-10 epilogue: two warps per TMEM
 // lane quadrant, 32 of the 64 output columns each (with one warp per quadrant the epilogue -- ~2700 cycles per 128-row
@@ -532,12 +539,14 @@ constexpr int kC2Smem = kC2BBytes + kC2Stages * kC2WinBytes + 256 + 1024;
 constexpr int kC2Threads = 11 * 32;
 static __global__ void __launch_bounds__(kC2Threads, 1)
 conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [128 x 32] SW64*/,
-                  const __grid_constant__ CUtensorMap tmap_b /*[64, 288] box [64 x 32] SW64*/, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmap_b /*[64, 288] box [64 x 32] SW64*/,
+                  const __grid_constant__ CUtensorMap tmap_c /*[n, 147, 147, 64] box [1, 1, 32, 32] SW64*/, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_smem = smem_base, win0 = smem_base + kC2BBytes;
-  const uint32_t bar_base = win0 + kC2Stages * kC2WinBytes;
+  const uint32_t out0 = win0 + kC2Stages * kC2WinBytes;
+  const uint32_t bar_base = out0 + kC2OutBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kC2Stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kC2Stages + a); };
@@ -545,13 +554,14 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
   const uint32_t b_bar = bar_base + 8u * (2 * kC2Stages + 2 * kC2AccStages);
   const uint32_t tmem_slot = b_bar + 8u;
   volatile uint32_t* tmem_slot_ptr =
-      (volatile uint32_t*)(smem_gen + kC2BBytes + kC2Stages * kC2WinBytes + 8 * (2 * kC2Stages + 2 * kC2AccStages + 1));
+      (volatile uint32_t*)(smem_gen + kC2BBytes + kC2Stages * kC2WinBytes + kC2OutBytes + 8 * (2 * kC2Stages + 2 * kC2AccStages + 1));
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = (p.M + kBM - 1) / kBM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < kC2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kC2AccStages; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     mbar_init(b_bar, 1);
@@ -616,17 +626,29 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
     const int quad = warp & 3;                     // TMEM lanes a warp may read: 32 * (warp % 4)
     const int half = warp >= 7 ? 1 : 0;            // columns [32 * half, +32)
     int as = 0; uint32_t aph = 0;
-    // per-channel BN constants (64 channels) in registers-by-load: read once
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m = tile * kBM + quad * 32 + lane;
-      bool row_ok = m < p.M;
-      long long orow = 0;
-      if (row_ok) {
-        const int img = m / p.in_hw, rem = m - img * p.in_hw;
-        const int y = rem / p.in_w, x = rem - y * p.in_w;
-        row_ok = (y < p.out_h) && (x < p.out_w);
-        orow = (long long)img * p.out_hw + (long long)y * p.out_w + x;
-      }
+    // Output path: the warp's 32 grid positions x 32 channels are staged as a [32 px][64 B] tile (SWIZZLE_64B, conflict-free
+    // 16-byte stores) and written by TMA.  (Per-lane 64-byte global stores cost 32 partial-sector L2 requests per
+    // instruction: the kernel ran at 2500 cycles per 128-pixel tile against 576 cycles of MMA work.)  The 32 positions are
+    // consecutive in the 149-wide input grid, so they break into at most two output-row segments.  The first is one TMA
+    // box at (x0, y): its rows past the end of the image row fall outside the 147-wide output and are clipped.  The lanes
+    // behind a row break (one warp in five has some) store their 64 bytes directly: a box with a negative start
+    // coordinate is rejected by the hardware (illegal instruction), and a box at x = 0 would write rows it does not own.
+    // Grid rows / columns >= 147 are never written, as before.
+    const int ew = (warp >= 7 ? warp - 3 : warp - 2);                 // 0..7
+    uint32_t li = 0;
+    // BN constants of this warp's 32 channels: lane-invariant, kept in registers
+    float sc[32], sh[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s4 = __ldg((const float4*)(p.scale + half * 32) + j), h4 = __ldg((const float4*)(p.shift + half * 32) + j);
+      sc[4 * j] = s4.x; sc[4 * j + 1] = s4.y; sc[4 * j + 2] = s4.z; sc[4 * j + 3] = s4.w;
+      sh[4 * j] = h4.x; sh[4 * j + 1] = h4.y; sh[4 * j + 2] = h4.z; sh[4 * j + 3] = h4.w;
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const int m0 = tile * kBM + quad * 32;                          // warp-uniform: first grid position of this warp
+      const int img0 = m0 / p.in_hw, rem0 = m0 - img0 * p.in_hw;
+      const int y0 = rem0 / p.in_w, x0 = rem0 - y0 * p.in_w;
+      const uint32_t stg = out0 + (uint32_t)((ew * 2 + (int)(li & 1u)) * kC2OutTile);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       uint32_t v[32];
@@ -635,31 +657,40 @@ conv3x3_is_kernel(const __grid_constant__ CUtensorMap tmap_a /*[rows, 32] box [1
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (row_ok) {
-        __nv_bfloat16* optr = p.out + orow * p.ldc + half * 32;
-        const float* scp = p.scale + half * 32;
-        const float* shp = p.shift + half * 32;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 s0 = __ldg((const float4*)(scp + g * 8)), s1 = __ldg((const float4*)(scp + g * 8 + 4));
-          const float4 h0 = __ldg((const float4*)(shp + g * 8)), h1 = __ldg((const float4*)(shp + g * 8 + 4));
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
-          }
-          uint4 o;
-          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          *(uint4*)(optr + g * 8) = o;
-        }
+      if (elect_one()) tma_store_wait_read1();                        // the store issued from this buffer two tiles ago has read it
+      __syncwarp();
+      __nv_bfloat16* direct_ptr = nullptr;                            // lanes behind a row break of the input grid
+      if (x0 + lane >= p.in_w && m0 + lane < p.M) {
+        int y1 = y0 + 1, img1 = img0;
+        if (y1 * p.in_w >= p.in_hw) { y1 = 0; ++img1; }
+        if (y1 < p.out_h) direct_ptr = p.out + ((long long)img1 * p.out_hw + (long long)y1 * p.out_w + (x0 + lane - p.in_w)) * p.ldc + half * 32;
       }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = g * 8 + 2 * j;
+          float f0 = __fadd_rn(__fmul_rn(__uint_as_float(v[c]), sc[c]), sh[c]);
+          float f1 = __fadd_rn(__fmul_rn(__uint_as_float(v[c + 1]), sc[c + 1]), sh[c + 1]);
+          if (p.relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(f1), "f"(f0));
+          else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(f1), "f"(f0));
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4))),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        if (direct_ptr) *(uint4*)(direct_ptr + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        if (m0 < p.M && y0 < p.out_h && x0 < p.out_w) tma_store_4d(&tmap_c, stg, half * 32, x0, y0, img0);
+        tma_store_commit();
+      }
+      __syncwarp();
       if (++as == kC2AccStages) { as = 0; aph ^= 1u; }
     }
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

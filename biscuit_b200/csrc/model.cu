@@ -76,7 +76,7 @@ int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uin
 
 // 4-D NHWC bf16 activation [N, H, W, C] with a [1, box_h, box_w, box_c] box, no swizzle (depthwise halo tiles)
 int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
-                   uint32_t box_h, uint32_t box_w, uint32_t box_c, bool swizzle128 = false) {
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c, bool swizzle128 = false, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {c, w, h, n};
@@ -84,7 +84,8 @@ int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, u
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
   return BQ_OK;
@@ -343,7 +344,7 @@ int launch_gemm(bq_model* m, const GemmParams& gp, const CUtensorMap& ta, const 
     if (!(gp.conv_mode && gp.N == 64 && gp.K == 288 && 2 * gp.in_w + 2 + 128 <= kC2WinRows))
       return bq_fail(ctx, BQ_ERR_ARG, "conv3x3_is_kernel: unsupported geometry");
     const int g2 = m_tiles < ctx->num_sms ? m_tiles : ctx->num_sms;
-    conv3x3_is_kernel<<<g2, kC2Threads, kC2Smem, ctx->stream>>>(ta, tb, gp);
+    conv3x3_is_kernel<<<g2, kC2Threads, kC2Smem, ctx->stream>>>(ta, tb, tc, gp);
   } else {
     if (!tb_half || gp.bn_box % 32 != 0 || gp.N > k2MaxN)
       return bq_fail(ctx, BQ_ERR_ARG, "gemm_tcgen05_2cta_kernel: unsupported N = %d (tile %d)", gp.N, gp.bn_box);
@@ -444,7 +445,9 @@ int build_plan(bq_model* m) {
     g.b_ptr = (const bf16*)m->conv2.w.p; g.ldb = 288;
     if ((rc = make_tmap(ctx, &op.ta, A.p(0), (uint64_t)s1 * s1 * B, 32, 32, 128, 32))) return rc;
     if ((rc = make_tmap(ctx, &op.tb, m->conv2.w.p, 64, 288, 288, 64, 32))) return rc;
-    op.tc = op.ta; op.tr = op.ta; op.tb2 = op.tb;      // unused by the direct-store epilogue
+    // output boxes of the epilogue warps: [1, 1, 32 pixels, 32 channels], SWIZZLE_64B staging tiles
+    if ((rc = make_tmap_nhwc(ctx, &op.tc, A.p(1), (uint64_t)B, (uint64_t)s2, (uint64_t)s2, 64, 1, 32, 32, false, true))) return rc;
+    op.tr = op.ta; op.tb2 = op.tb;
     op.Ho = s2; op.Wo = s2; op.Cout = 64;
     m->plan.push_back(op);
   }

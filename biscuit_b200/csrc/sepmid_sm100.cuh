@@ -29,8 +29,14 @@
 //   warps 2-9     epilogue per channel tile: tcgen05.ld -> BN scale/shift (per-lane constants: lane = channel)
 //                 (+ residual) (ReLU) -> bf16 -> [pixel][channel] staging -> TMA stores of the VALID pixels only
 //                 (one 19-pixel box per image row), so the zero border is never touched.
-// The accumulators are single-buffered (480 of 512 columns); the three channel tiles are released one by one, so the
-// next item's MMAs start on tile 0 while tiles 1 and 2 are still being drained.
+// The accumulators are single-buffered (480 of 512 columns), so a channel tile cannot take the next item's MMAs before
+// the epilogue has read it.  To keep the tensor pipe busy across item boundaries the three channel tiles are SKEWED by
+// one k-block: in step t the MMA warp issues (tile 0, k-block t), (tile 1, k-block t-1), (tile 2, k-block t-2) of one
+// continuous k-block stream over all items.  Tile 0 finishes an item two steps before tile 2, the three drains happen at
+// different times, and while one tile waits for its drain the other two still have MMAs to run (measured with the
+// tiles in lock-step: 28 % of the kernel was the tensor pipe waiting for the three drains in a row).  A depthwise
+// k-block therefore lives for three steps (4 stages), and the weight ring is a ring of single 128 x 64 tiles in exactly
+// the order the MMAs consume them.
 #pragma once
 
 #include "gemm_sm100.cuh"
@@ -50,16 +56,15 @@ constexpr int kWinRows = kCtaPx + 2 * (kPitch + 1);   // 122: halo of 21 rows on
 constexpr int kWinBytes = kWinRows * 128;       // 15,616
 constexpr int kNumKb = 12;                      // ceil(728 / 64); the last k-block holds 24 channels (2 k-steps)
 #ifndef BQ_SM_WST
-#define BQ_SM_WST 2          // weight ring depth in K-BLOCKS (a stage = the three 128 x 64 tiles of one k-block, 48 KB)
+#define BQ_SM_WST 5          // weight ring depth in TILES (128 x 64 bf16 = 16 KB per CTA and stage)
 #endif
 #ifndef BQ_SM_BST
-#define BQ_SM_BST 2
+#define BQ_SM_BST 4          // depthwise-output stages: a k-block lives for three MMA steps (the channel tiles are skewed)
 #endif
 constexpr int kWStages = BQ_SM_WST;
 constexpr int kWTile = 128 * 128;               // 128 weight rows x 64 k
-constexpr int kWBytes = 3 * kWTile;             // one ring stage: the three channel tiles of a k-block
 #ifndef BQ_SM_IST
-#define BQ_SM_IST 3
+#define BQ_SM_IST 2
 #endif
 #ifndef BQ_SM_EST
 #define BQ_SM_EST 3
@@ -71,7 +76,7 @@ constexpr int kStepPx = 40;                     // epilogue step: 40 pixels x 12
 constexpr int kOutTile = kStepPx * 64;          // one epilogue warp's tile of a step: [40 px][32 ch] bf16
 constexpr int kOutStep = 8 * kOutTile;          // the eight epilogue warps
 constexpr int kOffW = 0;
-constexpr int kOffB = kOffW + kWStages * kWBytes;
+constexpr int kOffB = kOffW + kWStages * kWTile;
 constexpr int kOffOut = kOffB + kBStages * kBBytes;
 constexpr int kEpiBufs = BQ_SM_EST;                     // rotating epilogue buffers: residual lands / in-place epilogue / store drains
 constexpr int kOffIn = kOffOut + kEpiBufs * kOutStep;
@@ -91,7 +96,7 @@ constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignm
 #define BQ_SM_EARLY 1          // epilogue hands a channel tile back before its first staging store
 #endif
 constexpr int kProducerWarps = BQ_SM_PW;
-constexpr int kThreads = 32 * (2 + 8 + kProducerWarps);   // warp 0 TMA, 1 MMA, 2-9 epilogue, 10.. producers (registers are granted per 4 warps: 18 cost as 20)
+constexpr int kThreads = 32 * (3 + 8 + kProducerWarps);   // warp 0 weight TMA, 1 MMA, 2-9 epilogue, 10.. producers, last: window TMA (registers are granted per 4 warps: 19 cost as 20)
 constexpr int kStripPx = kCtaPx / (kProducerWarps * 2);   // 16 channel groups x 20 strips of 4 consecutive pixels
 constexpr int kEpiWarps = 8;
 constexpr int kSlackRows = 2 * kItemPx;         // rows allocated past the last image (the last item may overhang)
@@ -162,6 +167,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
   return r;
 }
 
+// Issue order inside MMA step t (shared by the TMA and the MMA warp): slot j -> channel tile, or -1.  Tile ct works on
+// stream position t - ct; the one group that STARTS an item (k-block 0: it must wait for the epilogue) is issued last so
+// that the other two never queue behind that wait.
+__device__ __forceinline__ int step_tile(int t, int j, int U) {
+  int first = -1;                                     // the tile whose k-block is 0 in this step, if any
+#pragma unroll
+  for (int ct = 0; ct < 3; ++ct) {
+    const int u = t - ct;
+    if (u >= 0 && u < U && u % kNumKb == 0) first = ct;
+  }
+  int n = 0;
+#pragma unroll
+  for (int ct = 0; ct < 3; ++ct) {
+    const int u = t - ct;
+    if (u < 0 || u >= U || ct == first) continue;
+    if (n == j) return ct;
+    ++n;
+  }
+  return (first >= 0 && n == j) ? first : -1;
+}
+
 template <bool RELU_IN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box [122 x 64], no swizzle*/,
@@ -219,37 +245,20 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     // ===================== TMA: input window of this CTA's 80 pixels + its 128 rows of each weight tile =====================
     // (converged warp, one elected lane issues: TMA instructions take uniform-register operands like tcgen05.mma)
     {
-      int is = 0; uint32_t iph = 0;
       int ws = 0; uint32_t wph = 0;
-      for (int li = 0; li < my_items; ++li) {
-        const int p0 = (cluster_id + li * num_clusters) * kItemPx;
-#pragma unroll 1
-        for (int kb = 0; kb < kNumKb; ++kb) {
-          mbar_wait(in_empty(is), iph ^ 1u);
-          if (elect_one()) {
-#ifdef BQ_SM_DIAG_NOWIN       // TIMING DIAGNOSTIC ONLY (wrong results): no input-window traffic
-            mbar_arrive(in_full(is));
-#else
-            mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
-            tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), kb * 64,
-                        p0 + (int)rank * kCtaPx - (kPitch + 1));
-#endif
-          }
-          __syncwarp();
-          if (++is == kInStages) { is = 0; iph ^= 1u; }
+      const int U = my_items * kNumKb;                 // length of this cluster's k-block stream
+      for (int t = 0; t < U + 2; ++t) {
+        // weight tiles in MMA issue order (see the MMA warp): the group that starts an item goes last
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int ct = step_tile(t, j, U);
+          if (ct < 0) continue;
+          const int kb = (t - ct) % kNumKb;
           mbar_wait(w_empty(ws), wph ^ 1u);
           if (elect_one()) {
-#ifdef BQ_SM_DIAG_W1          // TIMING DIAGNOSTIC ONLY (wrong results): fetch one of the three weight tiles per k-block
             if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWTile);
             else mbar_arrive_remote(w_full(ws), 0);
-            for (int ct = 0; ct < 1; ++ct)
-#else
-            if (is_leader) mbar_expect_tx(w_full(ws), 2u * kWBytes);
-            else mbar_arrive_remote(w_full(ws), 0);
-#pragma unroll
-            for (int ct = 0; ct < 3; ++ct)
-#endif
-              tma_load_2d_2cta(smem_base + kOffW + ws * kWBytes + ct * kWTile, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
+            tma_load_2d_2cta(smem_base + kOffW + ws * kWTile, &tmap_w, w_full(ws), kb * 64, ct * 256 + (int)rank * 128);
           }
           __syncwarp();
           if (++ws == kWStages) { ws = 0; wph ^= 1u; }
@@ -261,56 +270,57 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     if (is_leader) {
       const uint32_t idesc = make_idesc(256, kItemPx);
       int ws = 0; uint32_t wph = 0;
-      int bs = 0; uint32_t bph = 0;
-      for (int li = 0; li < my_items; ++li) {
-#pragma unroll 1
-        for (int kb = 0; kb < kNumKb; ++kb) {
-          mbar_wait(b_full(bs), bph);
+      const int U = my_items * kNumKb;
+#ifdef BQ_SM_DIAG_STALL
+      long long st_b = 0, st_w = 0, st_a = 0;
+      const long long st_t0 = clock64();
+#endif
+      for (int t = 0; t < U + 2; ++t) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int ct = step_tile(t, j, U);
+          if (ct < 0) continue;
+          const int u = t - ct;                        // position in the k-block stream
+          const int li = u / kNumKb, kb = u - li * kNumKb;
+          const int bs = u % kBStages;
+#ifdef BQ_SM_DIAG_STALL         // TIMING DIAGNOSTIC ONLY: where the MMA issuer waits
+          const long long c0 = clock64();
+          mbar_wait(b_full(bs), (uint32_t)(u / kBStages) & 1u);
+          const long long c1 = clock64();
           mbar_wait(w_full(ws), wph);
+          const long long c2 = clock64();
+          if (kb == 0) mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
+          const long long c3 = clock64();
+          st_b += c1 - c0; st_w += c2 - c1; st_a += c3 - c2;
+#else
+          mbar_wait(b_full(bs), (uint32_t)(u / kBStages) & 1u);
+          mbar_wait(w_full(ws), wph);
+          if (kb == 0) mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);   // the epilogue has handed this tile back
+#endif
           tc_fence_after();
           const uint64_t db = make_smem_desc<128>(smem_base + kOffB + bs * kBBytes);
-          const uint64_t da0 = make_smem_desc<128>(smem_base + kOffW + ws * kWBytes);
-          if (kb == 0) {
-            // first k-block of an item: each channel tile starts as soon as the epilogue has handed IT back
-#pragma unroll
-            for (int ct = 0; ct < 3; ++ct) {
-              mbar_wait(acc_empty(ct), ((uint32_t)li & 1u) ^ 1u);
-              tc_fence_after();
-              const uint64_t da = da0 + (uint64_t)(ct * (kWTile >> 4));
-              const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
-              if (elect_one()) {
-                umma_bf16_2cta(d, da, db, idesc, 0u);
-                umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
-                umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
-                umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
-                if (ct == 2) { umma_commit_2cta(w_empty(ws)); umma_commit_2cta(b_empty(bs)); }
-              }
-              __syncwarp();
+          const uint64_t da = make_smem_desc<128>(smem_base + kOffW + ws * kWTile);
+          const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
+          if (elect_one()) {
+            umma_bf16_2cta(d, da, db, idesc, kb ? 1u : 0u);
+            umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
+            if (kb != kNumKb - 1) {                    // the last k-block holds 24 channels: two k-steps
+              umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
+              umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
             }
-          } else {
-            if (elect_one()) {
-#pragma unroll
-              for (int ct = 0; ct < 3; ++ct) {
-                const uint64_t da = da0 + (uint64_t)(ct * (kWTile >> 4));
-                const uint32_t d = tmem_base + (uint32_t)(ct * kItemPx);
-                umma_bf16_2cta(d, da, db, idesc, 1u);
-                umma_bf16_2cta(d, da + 2u, db + 2u, idesc, 1u);
-                if (kb != kNumKb - 1) {              // the last k-block holds 24 channels: two k-steps
-                  umma_bf16_2cta(d, da + 4u, db + 4u, idesc, 1u);
-                  umma_bf16_2cta(d, da + 6u, db + 6u, idesc, 1u);
-                } else {
-                  umma_commit_2cta(acc_full(ct));
-                }
-              }
-              umma_commit_2cta(w_empty(ws));
-              umma_commit_2cta(b_empty(bs));
-            }
-            __syncwarp();
+            umma_commit_2cta(w_empty(ws));
+            if (ct == 2) umma_commit_2cta(b_empty(bs));          // tile 2 is the last reader of a depthwise k-block
+            if (kb == kNumKb - 1) umma_commit_2cta(acc_full(ct));
           }
+          __syncwarp();
           if (++ws == kWStages) { ws = 0; wph ^= 1u; }
-          if (++bs == kBStages) { bs = 0; bph ^= 1u; }
         }
       }
+#ifdef BQ_SM_DIAG_STALL
+      if (lane == 0 && (cluster_id == 0 || cluster_id == 37))
+        printf("sepmid stall cluster %d items %d: total %lld  b_full %lld  w_full %lld  acc_empty %lld\n", cluster_id, my_items,
+               clock64() - st_t0, st_b, st_w, st_a);
+#endif
     }
   } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue: 128 channels (TMEM lanes) x 160 pixels (columns) per channel tile =====================
@@ -542,6 +552,26 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     }
     if (elect_one()) tma_store_wait_all();
     __syncwarp();
+  } else if (warp == 2 + kEpiWarps + kProducerWarps) {
+    // ===================== TMA: input window of this CTA's 80 pixels, one per k-block of the stream =====================
+    // (its own warp: behind the weight ring's waits the window requests were issued late and the producers starved)
+    int is = 0; uint32_t iph = 0;
+    const int U = my_items * kNumKb;
+    for (int t = 0; t < U; ++t) {
+      const int p0 = (cluster_id + (t / kNumKb) * num_clusters) * kItemPx;
+      mbar_wait(in_empty(is), iph ^ 1u);
+      if (elect_one()) {
+#ifdef BQ_SM_DIAG_NOWIN       // TIMING DIAGNOSTIC ONLY (wrong results): no input-window traffic
+        mbar_arrive(in_full(is));
+#else
+        mbar_expect_tx(in_full(is), (uint32_t)kWinBytes);
+        tma_load_2d(smem_base + kOffIn + is * kWinBytes, &tmap_in, in_full(is), (t % kNumKb) * 64,
+                    p0 + (int)rank * kCtaPx - (kPitch + 1));
+#endif
+      }
+      __syncwarp();
+      if (++is == kInStages) { is = 0; iph ^= 1u; }
+    }
   } else {
     // ===================== depthwise producers =====================
     const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
