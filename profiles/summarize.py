@@ -10,7 +10,7 @@ import os
 import sys
 from collections import OrderedDict
 
-FAMILY = [("sepconv2d_fused", "sepconv_fused"), ("sepconv_fused", "sepconv_fused"), ("gemm_tcgen05_2cta", "gemm_pointwise"), ("conv3x3_is", "gemm_conv2"), ("mc_head_fused", "head_fused"), ("gemm_tcgen05_kernel<32", "gemm_conv2"), ("gemm_tcgen05_kernel", "gemm_pointwise"),
+FAMILY = [("sepconv_mid", "sepconv_mid"), ("conv1_tc", "conv1"), ("pad_copy", "subsample"), ("sepconv2d_fused", "sepconv_fused"), ("sepconv_fused", "sepconv_fused"), ("gemm_tcgen05_2cta", "gemm_pointwise"), ("conv3x3_is", "gemm_conv2"), ("mc_head_fused", "head_fused"), ("gemm_tcgen05_kernel<32", "gemm_conv2"), ("gemm_tcgen05_kernel", "gemm_pointwise"),
           ("depthwise3x3", "depthwise"), ("maxpool_add", "maxpool_add"), ("subsample2", "subsample"), ("conv1_kernel", "conv1"),
           ("tile_stats", "tile_stats"), ("gap_kernel", "gap"), ("mc_expand", "mc_expand"), ("head_final", "head_final"),
           ("group_kahan", "threshold"), ("roc_", "threshold"), ("seg_bounds", "threshold"), ("group_apply", "threshold"),

@@ -168,14 +168,15 @@ def test_process_helpers(T):
 
 
 def test_config5_full_size_properties(T):
-    """2 M rows (10 folds x 100 slides x 2000 tiles): too slow to run the pandas oracle on every
-    fold in the GPU tier, so check one fold against the oracle and size-independent properties on
-    the rest: from_cv == (min, max, mean, mean) of per-fold detect; apply idempotent; percent_incl
-    consistent with the kept-slide frame; row-permutation invariance of detected thresholds."""
+    """2 M rows (10 folds x 100 slides x 2000 tiles): every fold against the oracle (the reference's
+    arithmetic needs ~0.1 s per 200 k-row fold), then size-independent properties: from_cv == (min,
+    max, mean, mean) of per-fold detect; apply idempotent; percent_incl consistent with the
+    kept-slide frame; row-permutation invariance of detected thresholds."""
     dfs = synth.cv_tables(k=10, n_slides=100, tiles_per_slide=2000)
     per = [T.detect(d.copy())[0] for d in dfs]
-    ref0 = O.detect(dfs[0].copy())[0]
-    assert_same_results(ref0, per[0], "fold 0 vs oracle")
+    for k, d in enumerate(dfs):
+        assert_same_results(O.detect(d.copy())[0], per[k], f"fold {k} vs oracle")
+    assert_same_results(O.from_cv([d.copy() for d in dfs]), T.from_cv([d.copy() for d in dfs]), "from_cv vs oracle")
     cv = T.from_cv([d.copy() for d in dfs])
     ok = [p for p in per if p["tile_uq"] is not None and p["slide_uq"] is not None]
     assert cv["tile_uq"] == min(p["tile_uq"] for p in ok)
@@ -193,6 +194,31 @@ def test_config5_full_size_properties(T):
     perm = dfs[1].sample(frac=1.0, random_state=0).reset_index(drop=True)
     pa = T.detect(perm)[0]
     assert pa["tile_uq"] == per[1]["tile_uq"] and pa["tile_pred"] == per[1]["tile_pred"]
+
+
+@pytest.mark.parametrize("dtype,ties", [(np.float32, 50), (np.float64, 50), (np.float64, None)],
+                         ids=["f32_ties", "f64_ties", "f64"])
+def test_config5_full_size_variants_vs_oracle(T, dtype, ties):
+    """SURVEY 8d's other config-5 tables at FULL fold size (200 k rows): the float64 (CSV-loaded) variant
+    and the heavy-ties variant (scores rounded to 1/50: thousands of equal scores per ROC boundary, equal
+    slide means), detect + apply on the detected thresholds, bit-for-bit against the oracle."""
+    dfs = synth.cv_tables(k=3, n_slides=100, tiles_per_slide=2000, seed0=40, dtype=dtype, ties=ties)
+    for k, d in enumerate(dfs):
+        want, got = O.detect(d.copy()), T.detect(d.copy())
+        assert_same_results(want[0], got[0], f"fold {k} thresholds")
+        assert same_scalar(want[1], got[1])
+    try:
+        cv_o = O.from_cv([d.copy() for d in dfs])
+    except Exception as e:  # every fold skipped: the product must raise the same error type
+        with pytest.raises(type(e)):
+            T.from_cv([d.copy() for d in dfs])
+        return
+    cv = T.from_cv([d.copy() for d in dfs])
+    assert_same_results(cv_o, cv, "from_cv")
+    big = pd.concat(dfs, ignore_index=True)
+    (ro, so), (rg, sg) = O.apply(big.copy(), **cv_o), T.apply(big.copy(), **cv)
+    assert_same_results(ro, rg, "apply")
+    assert_same_df(so, sg)
 
 
 def test_apply_sharded_single_rank_equals_apply(T):
