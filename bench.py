@@ -284,8 +284,13 @@ def run_native_arm(args, rank, world, local_rank):
         h2d = n * TILE_BYTES + n * (4 + 4 + 1 + 4)            # tiles + (y_pred, uncertainty, y_true, codes) table
         d2h = n * 2 * 4 * 2 + n * (8 + 1 + 1) + 64 * args.slides
         e2e = {"value": total_tiles / (ems / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ems / args.steps}
-        del host, host_np
+               "d2h_bytes_per_step": d2h, "ms_per_step": ems / args.steps, "host_memory": "pinned"}
+        # what a NumPy / DataFrame caller passes is PAGEABLE memory: two steps of the same call on a plain ndarray
+        pageable = np.array(host_np, copy=True)
+        one_step(pageable, 0)
+        pms, _ = timed(pageable, 2, 100)
+        e2e["pageable_value"] = n * 2 * world / (pms / 1e3)
+        del host, host_np, pageable
 
     if rank != 0:
         return None

@@ -1,5 +1,5 @@
 cp biscuit_b200/libbiscuit_b200.so /tmp/lib_default.so
-for f in profiles/variants/lib_a*.so; do
+for f in profiles/variants/lib_b*.so; do
   v=$(basename $f .so)
   cp $f biscuit_b200/libbiscuit_b200.so
   timeout 200 python bench.py --tiles 4096 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2> /tmp/err_$v.log | python -c "
