@@ -190,7 +190,8 @@ conv1_kernel(const TIn* __restrict__ tiles, const float* __restrict__ mean, cons
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 maxpool_add_kernel(const bf16* __restrict__ in, const bf16* __restrict__ res, bf16* __restrict__ out, int n_img,
-                   int H, int W, int Ho, int Wo, int C, int pad_top, int pad_left) {
+                   int H, int W, int Ho, int Wo, int C, int pad_top, int pad_left, int out_pitch = 0 /*0: dense [n, Ho, Wo, C];
+                   else pixel (y, x) of image b is row b * out_pitch^2 + y * out_pitch + x (zero-padded middle-flow layout)*/) {
   const int cv = C >> 3;
   const int64_t total = (int64_t)n_img * Ho * Wo * cv;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -235,13 +236,15 @@ maxpool_add_kernel(const bf16* __restrict__ in, const bf16* __restrict__ res, bf
     bf16x8_to_float(rv, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = __fadd_rn(m[j], r[j]);
-    *(uint4*)(out + o) = float_to_bf16x8(m);
+    const int64_t od = out_pitch ? (((int64_t)img * out_pitch + yo) * out_pitch + xo) * C + c8 * 8 : o;
+    *(uint4*)(out + od) = float_to_bf16x8(m);
   }
 }
 
 // stride-2 pixel gather: out[n,yo,xo,:] = in[n,2yo,2xo,:]   (1x1 stride-2 'valid' conv samples 0,2,4,...)
 __global__ void __launch_bounds__(256)
-subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n_img, int H, int W, int Ho, int Wo, int C) {
+subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n_img, int H, int W, int Ho, int Wo, int C,
+                  int in_pitch = 0 /*0: dense input; else the zero-padded layout with this row pitch*/) {
   const int cv = C >> 3;
   const int64_t total = (int64_t)n_img * Ho * Wo * cv;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -252,7 +255,8 @@ subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n_img
     pix /= Wo;
     const int yo = (int)(pix % Ho);
     const int img = (int)(pix / Ho);
-    const uint4 v = __ldg((const uint4*)(in + (((int64_t)img * H + 2 * yo) * W + 2 * xo) * C + c8 * 8));
+    const int64_t ip = in_pitch ? ((int64_t)img * in_pitch + 2 * yo) * in_pitch + 2 * xo : ((int64_t)img * H + 2 * yo) * W + 2 * xo;
+    const uint4 v = __ldg((const uint4*)(in + ip * C + c8 * 8));
     *(uint4*)(out + (((int64_t)img * Ho + yo) * Wo + xo) * C + c8 * 8) = v;
   }
 }

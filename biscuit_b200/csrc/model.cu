@@ -76,11 +76,13 @@ int make_tmap(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t rows, uin
 
 // 4-D NHWC bf16 activation [N, H, W, C] with a [1, box_h, box_w, box_c] box, no swizzle (depthwise halo tiles)
 int make_tmap_nhwc(bq_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t n, uint64_t h, uint64_t w, uint64_t c,
-                   uint32_t box_h, uint32_t box_w, uint32_t box_c, bool swizzle128 = false, bool swizzle64 = false) {
+                   uint32_t box_h, uint32_t box_w, uint32_t box_c, bool swizzle128 = false, bool swizzle64 = false,
+                   uint64_t pitch = 0 /*rows and columns of the (zero-padded) storage, 0 = dense*/) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return bq_fail(ctx, BQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {c, w, h, n};
-  cuuint64_t strides[3] = {c * sizeof(bf16), w * c * sizeof(bf16), h * w * c * sizeof(bf16)};
+  const uint64_t pw = pitch ? pitch : w, ph = pitch ? pitch : h;
+  cuuint64_t strides[3] = {c * sizeof(bf16), pw * c * sizeof(bf16), ph * pw * c * sizeof(bf16)};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -192,7 +194,7 @@ int load_dense(bq_ctx* ctx, const TensorIndex& ti, const std::string& name, int 
 // ------------------------------------------------------------------------------------------------
 // execution plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEP2D, OP_SEPMID, OP_PADCOPY };
+enum OpKind { OP_STATS, OP_CONV1, OP_GEMM, OP_DW, OP_POOLADD, OP_SUBSAMPLE, OP_GAP, OP_SEP2D, OP_SEPMID };
 
 struct Op {
   OpKind kind;
@@ -207,8 +209,8 @@ struct Op {
   const float* dw = nullptr;
   bq::sep2d::Sep2dParams s2;  // OP_SEP2D
   bq::sepmid::SepMidParams sm; // OP_SEPMID
-  int to_padded = 0;          // OP_PADCOPY direction
   bool padded_out = false;    // the op's output is in the zero-padded 20 x 20 layout (debug-stage copies strip it)
+  int in_pitch = 0, out_pitch = 0;   // OP_SUBSAMPLE input / OP_POOLADD output in the zero-padded layout (row pitch), 0 = dense
   // gemm
   GemmParams gp;
   int rows_per_tile = 0;      // M = rows_per_tile * batch
@@ -456,11 +458,12 @@ int build_plan(bq_model* m) {
 
   int dw_rc = BQ_OK;
   int n_dw = 0;
-  auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage) {
+  auto add_dw = [&](const bf16* in, bf16* out, int h, int c, int relu_in, const SepWeights& sw, int stage, int in_pitch = 0) {
     Op op; op.kind = OP_DW; op.stage = stage; op.in = in; op.out = out; op.H = h; op.W = h; op.C = c;
     op.relu_in = relu_in; op.dw = (const float*)sw.dw.p;
     const int CC = (c % 64 != 0) ? 56 : 64;                            // 728 = 13 x 56
-    int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwp::kHalo, bq::dwp::kHalo, CC);
+    int r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)c, bq::dwp::kHalo, bq::dwp::kHalo, CC,
+                           false, false, (uint64_t)in_pitch);
     if (r && !dw_rc) dw_rc = r;
     op.tag = "dw" + std::to_string(n_dw++);          // debug-stage name of the n-th stand-alone depthwise output
     op.Ho = h; op.Wo = h; op.Cout = c;
@@ -478,8 +481,8 @@ int build_plan(bq_model* m) {
   };
   // one SeparableConv2D (+BN, optional ReLU / residual): fused kernel for 728->728, otherwise depthwise + GEMM
   auto add_sep = [&](const bf16* in, bf16* dw_tmp, int h, int cin, int relu_in, const SepWeights& sw, bf16* out, int relu_out,
-                     const bf16* resid, int stage, const char* tag) -> int {
-    if (!m->use_simt && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
+                     const bf16* resid, int stage, const char* tag, int in_pitch = 0) -> int {
+    if (!in_pitch && !m->use_simt && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
       Op op; op.kind = OP_SEP2D; op.stage = stage;
       if (tag) op.tag = tag;
       op.in = in; op.out = out; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = sw.pw.cout;
@@ -493,39 +496,53 @@ int build_plan(bq_model* m) {
       m->plan.push_back(op);
       return BQ_OK;
     }
-    add_dw(in, dw_tmp, h, cin, relu_in, sw, stage);
+    add_dw(in, dw_tmp, h, cin, relu_in, sw, stage, in_pitch);
     return add_gemm(dw_tmp, h * h, sw.pw, out, relu_out, resid, stage, tag, h, sw.pw.cout);
   };
   // entry-style block with a strided 1x1 residual branch and a max-pool (blocks 2,3,4,13)
-  auto res_block = [&](int b, int cout1, int cout2, int relu_first, int stage) -> int {
+  // `padded_in` / `padded_out`: the block input / output lives in the zero-padded middle-flow layout (pitch 20), which
+  // saves the two layout-conversion copies around blocks 5-12
+  auto res_block = [&](int b, int cout1, int cout2, int relu_first, int stage, const bf16* padded_in = nullptr,
+                       bf16* padded_out = nullptr) -> int {
     int t[4]; others(X, t);
     const int Ho = (H + 1) / 2;
+    const bf16* xin = padded_in ? padded_in : A.p(X);
+    const int in_pitch = padded_in ? bq::sepmid::kPitch : 0;
     const SepWeights& s1w = *m->sep.at("block" + std::to_string(b) + "_sepconv1");
     const SepWeights& s2w = *m->sep.at("block" + std::to_string(b) + "_sepconv2");
     const PwWeights& rw = *m->res.at("block" + std::to_string(b) + "_res");
-    { Op op; op.kind = OP_SUBSAMPLE; op.stage = stage; op.in = A.p(X); op.out = A.p(t[0]); op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = C; m->plan.push_back(op); }
+    { Op op; op.kind = OP_SUBSAMPLE; op.stage = stage; op.in = xin; op.in_pitch = in_pitch; op.out = A.p(t[0]); op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = C; m->plan.push_back(op); }
     int r;
     if ((r = add_gemm(A.p(t[0]), Ho * Ho, rw, A.p(t[1]), 0, nullptr, stage, nullptr, Ho, cout2))) return r;   // res -> t1
-    if ((r = add_sep(A.p(X), A.p(t[0]), H, C, relu_first, s1w, A.p(t[2]), 1, nullptr, stage, nullptr))) return r;
+    if ((r = add_sep(xin, A.p(t[0]), H, C, relu_first, s1w, A.p(t[2]), 1, nullptr, stage, nullptr, in_pitch))) return r;
     if ((r = add_sep(A.p(t[2]), A.p(t[0]), H, cout1, 0, s2w, A.p(t[3]), 0, nullptr, stage, nullptr))) return r;
-    { Op op; op.kind = OP_POOLADD; op.stage = stage; op.in = A.p(t[3]); op.in2 = A.p(t[1]); op.out = A.p(X);
+    { Op op; op.kind = OP_POOLADD; op.stage = stage; op.in = A.p(t[3]); op.in2 = A.p(t[1]); op.out = padded_out ? padded_out : A.p(X);
+      op.out_pitch = padded_out ? bq::sepmid::kPitch : 0; op.padded_out = padded_out != nullptr;
       op.H = H; op.W = H; op.Ho = Ho; op.Wo = Ho; op.C = cout2; op.Cout = cout2; op.pad_top = same_pad_before(H); op.pad_left = same_pad_before(H);
       op.tag = "block" + std::to_string(b); m->plan.push_back(op); }
     H = Ho; C = cout2;
     return BQ_OK;
   };
-  if ((rc = res_block(2, 128, 128, 0, 2)) || (rc = res_block(3, 256, 256, 1, 2)) || (rc = res_block(4, 728, 728, 1, 2))) return rc;
-  // ---- middle flow: 8 x (3 x (ReLU, sepconv, BN)) + identity
-  if (m->sep_mid && H == bq::sepmid::kMap && C == bq::sepmid::kC) {
-    // Fused depthwise->pointwise kernel on the zero-padded flattened layout (sepmid_sm100.cuh).  The four buffers are
-    // dedicated to this layout: zeroed once here, and only VALID pixels are ever written, so the border stays zero.
+  if ((rc = res_block(2, 128, 128, 0, 2)) || (rc = res_block(3, 256, 256, 1, 2))) return rc;
+  // Fused depthwise->pointwise kernel on the zero-padded flattened layout (sepmid_sm100.cuh) for the middle flow.  The
+  // four buffers are dedicated to this layout: zeroed once here, and only VALID pixels are ever written, so the border
+  // stays zero.  Block 4's pool+add writes its output straight into that layout and block 13 reads it from there.
+  const bool mid = m->sep_mid && (H + 1) / 2 == bq::sepmid::kMap;
+  auto P = [&](int i) { return (bf16*)m->midbuf[i].p; };
+  if (mid) {
     using namespace bq::sepmid;
     const uint64_t rows = (uint64_t)B * kImgRows + kSlackRows;
     for (auto& b : m->midbuf) {
       if ((rc = bq_alloc(ctx, b, rows * kC * sizeof(bf16)))) return rc;
       BQ_CUDA(ctx, cudaMemset(b.p, 0, rows * kC * sizeof(bf16)));
     }
-    auto P = [&](int i) { return (bf16*)m->midbuf[i].p; };
+  }
+  if ((rc = res_block(4, 728, 728, 1, 2, nullptr, mid ? P(0) : nullptr))) return rc;
+  // ---- middle flow: 8 x (3 x (ReLU, sepconv, BN)) + identity
+  int mid_out = -1;                               // padded buffer holding the output of block 12
+  if (mid) {
+    using namespace bq::sepmid;
+    const uint64_t rows = (uint64_t)B * kImgRows + kSlackRows;
     auto add_mid = [&](int src, int dst, int res, const SepWeights& sw, int relu_in, int relu_out, const char* tag) -> int {
       Op op; op.kind = OP_SEPMID; op.stage = 3; op.padded_out = true;
       if (tag) op.tag = tag;
@@ -544,8 +561,6 @@ int build_plan(bq_model* m) {
       m->plan.push_back(op);
       return BQ_OK;
     };
-    { Op op; op.kind = OP_PADCOPY; op.stage = 3; op.in = A.p(X); op.out = P(0); op.to_padded = 1; op.padded_out = true;
-      op.H = kMap; op.W = kMap; op.C = kC; op.Ho = kMap; op.Wo = kMap; op.Cout = kC; m->plan.push_back(op); }
     int x = 0;                                   // padded buffer holding the block input (= residual)
     for (int b = 5; b <= 12; ++b) {
       const std::string pre = "block" + std::to_string(b) + "_sepconv";
@@ -557,8 +572,7 @@ int build_plan(bq_model* m) {
       if ((rc = add_mid(bb, c, x, w3, 0, 0, tag.c_str()))) return rc;
       x = c;
     }
-    { Op op; op.kind = OP_PADCOPY; op.stage = 3; op.in = P(x); op.out = A.p(X); op.to_padded = 0;
-      op.H = kMap; op.W = kMap; op.C = kC; op.Ho = kMap; op.Wo = kMap; op.Cout = kC; m->plan.push_back(op); }
+    mid_out = x;
   } else
   for (int b = 5; b <= 12; ++b) {
     int t[4]; others(X, t);
@@ -572,7 +586,7 @@ int build_plan(bq_model* m) {
     X = t[2];
   }
   // ---- exit flow
-  if ((rc = res_block(13, 728, 1024, 1, 4))) return rc;
+  if ((rc = res_block(13, 728, 1024, 1, 4, mid_out >= 0 ? P(mid_out) : nullptr))) return rc;
   {
     int t[4]; others(X, t);
     const SepWeights &w1 = *m->sep.at("block14_sepconv1"), &w2 = *m->sep.at("block14_sepconv2");
@@ -654,13 +668,13 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
     case OP_POOLADD: {
       KScope ks(m, BQ_K_POOLADD, 0, act * nb * op.C * ((double)op.H * op.W + 2.0 * op.Ho * op.Wo));
       bq::maxpool_add_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
-          op.in, op.in2, op.out + out_off, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left);
+          op.in, op.in2, op.out + out_off, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.pad_top, op.pad_left, op.out_pitch);
       break;
     }
     case OP_SUBSAMPLE: {
       KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.Ho * op.Wo * op.C);
       bq::subsample2_kernel<<<grid1d((int64_t)nb * op.Ho * op.Wo * (op.C / 8)), 256, 0, ctx->stream>>>(
-          op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C);
+          op.in, op.out, nb, op.H, op.W, op.Ho, op.Wo, op.C, op.in_pitch);
       break;
     }
     case OP_SEP2D: {
@@ -688,11 +702,6 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
         bq::sepmid::sepconv_mid_kernel<true><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sm);
       else
         bq::sepmid::sepconv_mid_kernel<false><<<2 * clusters, bq::sepmid::kThreads, bq::sepmid::kSmem, ctx->stream>>>(op.ta, op.tb, op.tc, op.tr, sm);
-      break;
-    }
-    case OP_PADCOPY: {
-      KScope ks(m, BQ_K_SUBSAMPLE, 0, 2 * act * nb * op.H * op.W * op.C);
-      bq::sepmid::pad_copy_kernel<<<grid1d((int64_t)nb * op.H * op.W * (op.C / 8)), 256, 0, ctx->stream>>>(op.in, op.out, nb, op.to_padded);
       break;
     }
     case OP_GAP: {
