@@ -4,14 +4,15 @@
 //
 // The CUDA-core kernel spent 432 FFMA2 per output pixel and ran at 13 % of the HBM roofline.  Here the layer is an implicit
 // GEMM  D[128 px, 32] = A[128 px, 3 x (27 -> 32)] * B[32, 96]^T  issued as six tcgen05.mma (K = 16 each) per 128 pixels:
-//   * A holds the RAW uint8 pixels converted to bf16 -- integers 0..255 are exact in bf16;
+//   * A holds the uint8 pixels minus m0 = round(tile mean) as bf16 -- integers in [-255, 255] are exact in bf16 (removing
+//     the common term up front keeps the accumulators small: exactly 0 on a constant tile);
 //   * B holds the fp32 filter split into THREE bf16 terms  w = hi + mid + lo  (3 x 8 significand bits = fp32's 24) laid
 //     along K: the same A stage is multiplied with the hi, mid and lo rows in turn and all three accumulate into ONE fp32
 //     TMEM tile.  Every product is exact in fp32, so the accumulator holds the fp32 convolution of the raw pixels up to
 //     fp32 summation rounding;
 //   * the standardisation is affine and the layer is bias-free and 'valid', so it moves behind the convolution together
-//     with the folded BatchNorm:  BN(conv(W, (x - m) / sd)) = conv(W, x) * g + h,  g = scale / sd,
-//     h = shift - m * sum(W) * g, computed per tile in fp64 by tile_stats_kernel; the epilogue is one FMA + ReLU.
+//     with the folded BatchNorm:  BN(conv(W, (x - m) / sd)) = conv(W, x - m0) * g + h,  g = scale / sd,
+//     h = shift - (m - m0) * sum(W) * g, computed per tile in fp64 by tile_stats_kernel; the epilogue is one FMA + ReLU.
 //
 // Persistent CTAs (two per SM), one work item = 128 consecutive output pixels of one image (<= 2 output rows):
 //   warp 9     loader: the <= 5 input rows of an item are ONE contiguous byte range of the tile buffer -> one 1-D bulk copy
@@ -56,6 +57,7 @@ constexpr int kThreads = 10 * 32;
 struct Conv1Params {
   const uint8_t* tiles;     // [n, 299, 299, 3]
   const float* affine;      // [n][64]: g[32] | h[32] per tile (tile_stats_kernel)
+  const float* m0;          // [n]: round(tile mean), subtracted from every pixel by the producers
   const bf16* w;            // [96][32] bf16 K-major: row = part * 32 + channel, k = tap * 3 + ci (27..31 zero)
   bf16* out;                // [n, 149, 149, 32]
   int n_img;
@@ -181,6 +183,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmap_out /*[n * 22201, 32] b
       const int p0 = (it - img * kItemsPerImg) * 128;
       const int oy0 = p0 / kOut;
       const int pix = p0 + ptid;
+      const float magic = __fadd_rn(8388608.f, __ldg(p.m0 + img));  // 2^23 + m0: exact (an integer below 2^24)
       mbar_wait(in_full(si), (li / kInStages) & 1u);
       mbar_wait(a_empty(s), ph ^ 1u);
       uint32_t packed[16];
@@ -189,7 +192,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmap_out /*[n * 22201, 32] b
       if (pix < kPx) {
         const int oy = pix / kOut, ox = pix - oy * kOut;
         const uint32_t o0 = (uint32_t)(delta + (2 * (oy - oy0)) * kRowBytes + ox * 6);
-        uint32_t f[28];                                             // fp32 bit patterns of the 27 pixels values (+ 0)
+        uint32_t f[28];                                             // fp32 bit patterns of the 27 values x - m0 (+ 0)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const uint32_t o = o0 + (uint32_t)(ky * kRowBytes);
@@ -198,12 +201,12 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmap_out /*[n * 22201, 32] b
           const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
           const uint32_t a[3] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), w2 >> sh};
 #pragma unroll
-          for (int j = 0; j < 9; ++j)       // byte -> 0x4B0000bb = 2^23 + b; minus 2^23 is exact
-            f[ky * 9 + j] = __float_as_uint(__fadd_rn(__uint_as_float(__byte_perm(a[j >> 2], 0x4B000000u, 0x7440u | (uint32_t)(j & 3))), -8388608.f));
+          for (int j = 0; j < 9; ++j)       // byte -> 0x4B0000bb = 2^23 + b; minus (2^23 + m0) is exact: b - m0
+            f[ky * 9 + j] = __float_as_uint(__fadd_rn(__uint_as_float(__byte_perm(a[j >> 2], 0x4B000000u, 0x7440u | (uint32_t)(j & 3))), -magic));
         }
         f[27] = 0u;
 #pragma unroll
-        for (int k = 0; k < 14; ++k) packed[k] = __byte_perm(f[2 * k], f[2 * k + 1], 0x7632u);   // upper halves: exact bf16 of 0..255
+        for (int k = 0; k < 14; ++k) packed[k] = __byte_perm(f[2 * k], f[2 * k + 1], 0x7632u);   // upper halves: exact bf16 of -255..255
       }
       uint8_t* a_row = smem_gen + kOffA + s * kABytes + ptid * 64;
       const int sw = (ptid >> 1) & 3;

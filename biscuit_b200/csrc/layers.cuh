@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(512)
 tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, float* __restrict__ mean,
                   float* __restrict__ inv_std, const float* __restrict__ c1_sumw = nullptr,
                   const float* __restrict__ c1_scale = nullptr, const float* __restrict__ c1_shift = nullptr,
-                  float* __restrict__ c1_affine = nullptr /*[n][64]: per-tile (g, h) of conv1_tc_kernel's epilogue*/) {
+                  float* __restrict__ c1_affine = nullptr /*[n][64]: per-tile (g, h) of conv1_tc_kernel's epilogue*/,
+                  float* __restrict__ c1_m0 = nullptr /*[n]: the integer the producers subtract from every pixel*/) {
   const uint8_t* src = tiles + (int64_t)blockIdx.x * bytes_per_tile;
   unsigned long long s = 0, s2 = 0;
   // head up to 16-byte alignment, vector body, tail
@@ -96,14 +97,22 @@ tile_stats_kernel(const uint8_t* __restrict__ tiles, int64_t bytes_per_tile, flo
     stat[0] = m; stat[1] = 1.0 / sd;
   }
   if (c1_affine) {
-    // block1_conv1 is bias-free and 'valid': BN(conv(W, (x - m) / sd)) = conv(W, x) * g + h with, per output channel,
-    // g = scale / sd and h = shift - m * sum(W) * g  (fp64 here, one fp32 FMA per output in the kernel)
+    // block1_conv1 is bias-free and 'valid': BN(conv(W, (x - m) / sd)) = conv(W, x - m0) * g + h with, per output channel,
+    // g = scale / sd and h = shift - (m - m0) * sum(W) * g  (fp64 here, one fp32 FMA per output in the kernel).
+    // m0 = round(m) is removed from the pixels BEFORE the convolution (x - m0 is an integer in [-255, 255]: still exact in
+    // bf16), so the convolution never carries a large common term that the epilogue would have to cancel: on a constant
+    // tile the accumulators are exactly 0, and on low-contrast tiles 1 / sd does not amplify fp32 summation rounding.
+    // m and 1 / sd enter as the SAME fp32 values the standardise-first arithmetic uses (tf.image.per_image_standardization
+    // and the oracle subtract an fp32 mean): on a tile where one pixel differs the fp32 mean is the constant itself.
     __syncthreads();
+    const double mf = (double)(float)stat[0], isf = (double)(float)stat[1];
+    const double m0 = rint(mf);
+    if (threadIdx.x == 0) c1_m0[blockIdx.x] = (float)m0;
     if (threadIdx.x < 32) {
       const int c = threadIdx.x;
-      const double g = stat[1] * (double)c1_scale[c];
+      const double g = isf * (double)c1_scale[c];
       c1_affine[(int64_t)blockIdx.x * 64 + c] = (float)g;
-      c1_affine[(int64_t)blockIdx.x * 64 + 32 + c] = (float)((double)c1_shift[c] - stat[0] * (double)c1_sumw[c] * g);
+      c1_affine[(int64_t)blockIdx.x * 64 + 32 + c] = (float)((double)c1_shift[c] - (mf - m0) * (double)c1_sumw[c] * g);
     }
   }
 }

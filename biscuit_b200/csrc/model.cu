@@ -245,7 +245,7 @@ struct bq_model {
   // weights
   DevBuf conv1_w, conv1_scale, conv1_shift;    // fp32 [27][32], [32], [32]
   DevBuf conv1_wtc, conv1_sumw;                // tensor-core form of the same filter: bf16 [96][32] (hi | mid | lo thirds of fp32), fp32 [32] tap sums
-  DevBuf conv1_affine;                         // fp32 [max_batch][64]: per-tile epilogue constants of conv1_tc_kernel (tile_stats_kernel)
+  DevBuf conv1_affine, conv1_m0;               // fp32 [max_batch][64] + [max_batch]: per-tile constants of conv1_tc_kernel (tile_stats_kernel)
   PwWeights conv2;
   std::map<std::string, std::unique_ptr<SepWeights>> sep;
   std::map<std::string, std::unique_ptr<PwWeights>> res;
@@ -418,7 +418,7 @@ int build_plan(bq_model* m) {
   int rc;
   if ((rc = bq_alloc(ctx, m->tiles_dev, (size_t)B * px * px * 3 + 64)) ||
       (rc = bq_alloc(ctx, m->tiles_dev2, (size_t)B * px * px * 3 + 64)) || (rc = bq_alloc(ctx, m->mean, B * 4)) ||
-      (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->conv1_affine, (size_t)B * 64 * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
+      (rc = bq_alloc(ctx, m->inv_std, B * 4)) || (rc = bq_alloc(ctx, m->conv1_affine, (size_t)B * 64 * 4)) || (rc = bq_alloc(ctx, m->conv1_m0, (size_t)B * 4)) || (rc = bq_alloc(ctx, m->feat, (size_t)B * kFeatures * 4)) ||
       (rc = bq_alloc(ctx, m->feat_bf16, (size_t)B * kFeatures * 2)) ||
       (rc = bq_alloc(ctx, m->out_mean, (size_t)m->head_batch * m->cfg.n_classes * 4)) ||
       (rc = bq_alloc(ctx, m->out_std, (size_t)m->head_batch * m->cfg.n_classes * 4)))
@@ -615,7 +615,7 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       bq::tile_stats_kernel<<<nb, 512, 0, ctx->stream>>>(m->tiles_src, (int64_t)px * px * 3,
                                                         (float*)m->mean.p, (float*)m->inv_std.p, (const float*)m->conv1_sumw.p,
                                                         (const float*)m->conv1_scale.p, (const float*)m->conv1_shift.p,
-                                                        (float*)m->conv1_affine.p);
+                                                        (float*)m->conv1_affine.p, (float*)m->conv1_m0.p);
       break;
     }
     case OP_CONV1: {
@@ -624,7 +624,7 @@ int run_op(bq_model* m, Op& op, int nb, int64_t out_off = 0) {
       if (!m->input_f32 && !m->use_simt && px == bq::conv1tc::kIn) {
         // raw uint8 pixels on the tensor cores, standardisation applied behind the convolution (conv1_sm100.cuh)
         bq::conv1tc::Conv1Params cp;
-        cp.tiles = m->tiles_src; cp.affine = (const float*)m->conv1_affine.p;
+        cp.tiles = m->tiles_src; cp.affine = (const float*)m->conv1_affine.p; cp.m0 = (const float*)m->conv1_m0.p;
         cp.w = (const bf16*)m->conv1_wtc.p; cp.out = op.out; cp.n_img = nb;
         const int items = nb * bq::conv1tc::kItemsPerImg;
         const int g1 = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;

@@ -70,6 +70,42 @@ def test_backbone_stage_parity(iface, tiles, oracle_bf16, stage):
     assert d.mean() <= 2.5e-2 * np.abs(ref).mean(), stats
 
 
+def test_entry_conv_on_degenerate_tiles(weights):
+    """block1_conv1 runs on the tensor cores with the standardisation moved behind the convolution (conv1_sm100.cuh).
+    That is only safe if the convolution never carries a large common term: constant tiles (blank background: std = 0,
+    so 1 / max(std, 1/sqrt(N)) = 518), near-constant tiles, black / white tiles and a high-contrast checkerboard must
+    match the oracle (which standardises first, in fp32) to bf16 rounding -- at most one bf16 ulp, on few outputs."""
+    import torch
+    from biscuit_b200.uq import UncertaintyInterface
+    rng = np.random.default_rng(5)
+    t = np.zeros((8, 299, 299, 3), np.uint8)
+    t[0] = 255                                            # white background
+    t[1] = 0                                              # black
+    t[2] = 237                                            # constant, odd value
+    t[3] = 200; t[3, 150, 150, 1] = 201                   # a single pixel differs: std = 0.0019
+    t[4] = 128 + (rng.random((299, 299, 3)) < 0.02)       # sparse +1 noise
+    t[5] = (np.indices((299, 299)).sum(0) % 2 * 255).astype(np.uint8)[..., None]   # checkerboard 0 / 255
+    t[6] = rng.integers(0, 256, (299, 299, 3), dtype=np.uint8)
+    t[7] = rng.integers(250, 256, (299, 299, 3), dtype=np.uint8)                   # bright, low contrast
+    it = UncertaintyInterface(weights, max_batch=8)
+    got = it.debug_stage(t, "block1_conv1")
+    o = X.XceptionUQOracle(weights, emulate_bf16=True)
+    stages = {}
+    with torch.no_grad():
+        o.backbone(t, stages=stages)
+    ref = stages["block1_conv1"]
+    assert got.shape == ref.shape
+    for i in range(len(t)):
+        d = np.abs(got[i] - ref[i])
+        # one bf16 ulp is <= 2^-7 relative; the absolute floor covers outputs that sit on the ReLU boundary
+        # (pre-activations of +-1e-6 land on 0 on one side and on a tiny positive number on the other)
+        ulp = np.maximum(np.maximum(np.abs(ref[i]), np.abs(got[i])) * 2.0 ** -7, 1e-5)
+        bad = d > ulp * 1.01
+        assert not bad.any(), (i, float(d.max()), float(np.abs(ref[i]).max()), int(bad.sum()))
+        assert (d > 0).mean() <= 0.02, (i, float((d > 0).mean()))          # and only a few outputs differ at all
+    it.close()
+
+
 def test_features_and_uq_with_injected_masks(iface, tiles, oracle_bf16, weights):
     o, _, feats_ref = oracle_bf16
     masks = X.keep_masks(N_TILES, T, 1024, 0.1, SEED)
