@@ -92,9 +92,6 @@ constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignm
 #ifndef BQ_SM_EPI_V2
 #define BQ_SM_EPI_V2 1         // epilogue on accumulator fragments (tcgen05.ld.16x256b + stmatrix.trans) instead of one lane per channel
 #endif
-#ifndef BQ_SM_PFD
-#define BQ_SM_PFD 0            // L2 prefetch distance of the input windows, in k-blocks (0 = off)
-#endif
 #ifndef BQ_SM_EARLY
 #define BQ_SM_EARLY 1          // epilogue hands a channel tile back before its first staging store
 #endif
@@ -560,20 +557,8 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     // (its own warp: behind the weight ring's waits the window requests were issued late and the producers starved)
     int is = 0; uint32_t iph = 0;
     const int U = my_items * kNumKb;
-    auto win_row = [&](int t) { return (cluster_id + (t / kNumKb) * num_clusters) * kItemPx + (int)rank * kCtaPx - (kPitch + 1); };
-#if BQ_SM_PFD > 0
-    // The windows come from DRAM (the layer input is 300 MB per launch) and only two are in flight per CTA: request the
-    // boxes of the next BQ_SM_PFD k-blocks into L2 ahead of the ring, so that the ring's own loads are L2 hits.
-    if (elect_one())
-      for (int t = 0; t < BQ_SM_PFD && t < U; ++t) tma_prefetch_2d(&tmap_in, (t % kNumKb) * 64, win_row(t));
-    __syncwarp();
-#endif
     for (int t = 0; t < U; ++t) {
       const int p0 = (cluster_id + (t / kNumKb) * num_clusters) * kItemPx;
-#if BQ_SM_PFD > 0
-      if (t + BQ_SM_PFD < U && elect_one()) tma_prefetch_2d(&tmap_in, ((t + BQ_SM_PFD) % kNumKb) * 64, win_row(t + BQ_SM_PFD));
-      __syncwarp();
-#endif
       mbar_wait(in_empty(is), iph ^ 1u);
       if (elect_one()) {
 #ifdef BQ_SM_DIAG_NOWIN       // TIMING DIAGNOSTIC ONLY (wrong results): no input-window traffic
