@@ -1138,7 +1138,6 @@ static int predict_impl(bq_model* m, const uint8_t* tiles, bool f32_input, int64
     if (tiles_on_dev) {
       m->tiles_src = tiles + (size_t)i0 * tile_bytes;
     } else {
-      if (i0 + B < n && (rc = issue_copy(i0 + B, slot ^ 1))) return rc;
       BQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copied[slot], 0));
       m->tiles_src = stage[slot];
     }
@@ -1159,7 +1158,13 @@ static int predict_impl(bq_model* m, const uint8_t* tiles, bool f32_input, int64
       m->tiles_src = (const uint8_t*)m->tiles_norm.p;
     }
     if ((rc = run_backbone_graphed(m, nb))) return rc;
-    if (!tiles_on_dev) BQ_CUDA(ctx, cudaEventRecord(m->consumed[slot], ctx->stream));
+    if (!tiles_on_dev) {
+      BQ_CUDA(ctx, cudaEventRecord(m->consumed[slot], ctx->stream));
+      // The next micro-batch's copy is issued AFTER this one's backbone is queued: a copy from PAGEABLE memory blocks the
+      // calling thread while the driver stages it, and that time must fall under queued GPU work (from pinned memory the
+      // call returns at once and the order makes no difference).
+      if (i0 + B < n && (rc = issue_copy(i0 + B, slot ^ 1))) return rc;
+    }
     if (features && (rc = bq_from_device(ctx, features + (size_t)i0 * kFeatures, m->feat.p, (size_t)nb * kFeatures * 4)))
       return rc;
     const bool last = i0 + B >= n;
