@@ -22,8 +22,8 @@
 //
 // Work item = 160 consecutive padded rows (8 padded image rows) per CTA pair; per 64-channel k-block and CTA:
 //   warp 0        TMA: the (80 + 42)-row input window of this CTA's 80 pixels, and three 128 x 64 weight tiles
-//   warps 10-19   depthwise producers: thread = (4 channels, 4 consecutive pixels), the three row triplets slide in
-//                 registers (3 LDS.64 + 18 FFMA2 per output, same tap order as depthwise3x3_pipe_kernel) -> bf16 ->
+//   warps 10-13   depthwise producers: thread = 4 channels x (2 image rows x 5 columns); the 4 x 7 halo is read once
+//                 (28 LDS.64 + 180 FFMA2 per 10 outputs, same tap order as depthwise3x3_pipe_kernel) -> bf16 ->
 //                 this CTA's half of the 128B-swizzled N-side stage
 //   warp 1        (leader CTA) 3 x 4 tcgen05.mma.cta_group::2 (M = 256, N = 160, K = 16) per k-block
 //   warps 2-9     epilogue per channel tile: tcgen05.ld -> BN scale/shift (per-lane constants: lane = channel)
@@ -83,21 +83,15 @@ constexpr int kOffIn = kOffOut + kEpiBufs * kOutStep;
 constexpr int kOffBar = kOffIn + kInStages * kWinBytes;
 constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignment of the base
 // developer tunables (profiles/build_variants.py builds A/B copies of the library with -D overrides)
-#ifndef BQ_SM_PW
-#define BQ_SM_PW 8             // producer warps: 8 (5-pixel strips) or 10 (4-pixel strips)
-#endif
-#ifndef BQ_SM_SWPIPE
-#define BQ_SM_SWPIPE 0         // explicit software pipelining of the window loads + tap prefetch in the producers
-#endif
+constexpr int kProducerWarps = 4;               // 128 threads = 16 channel groups x (2 image-row pairs x 4 column strips)
+constexpr int kColsPerStrip = 5;                // 4 strips x 5 columns = the 20-pixel padded row
 #ifndef BQ_SM_EPI_V2
 #define BQ_SM_EPI_V2 1         // epilogue on accumulator fragments (tcgen05.ld.16x256b + stmatrix.trans) instead of one lane per channel
 #endif
 #ifndef BQ_SM_EARLY
 #define BQ_SM_EARLY 1          // epilogue hands a channel tile back before its first staging store
 #endif
-constexpr int kProducerWarps = BQ_SM_PW;
 constexpr int kThreads = 32 * (3 + 8 + kProducerWarps);   // warp 0 weight TMA, 1 MMA, 2-9 epilogue, 10.. producers, last: window TMA (registers are granted per 4 warps: 19 cost as 20)
-constexpr int kStripPx = kCtaPx / (kProducerWarps * 2);   // 16 channel groups x 20 strips of 4 consecutive pixels
 constexpr int kEpiWarps = 8;
 constexpr int kSlackRows = 2 * kItemPx;         // rows allocated past the last image (the last item may overhang)
 
@@ -574,23 +568,22 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     }
   } else {
     // ===================== depthwise producers =====================
-    const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
-    const int c4 = ptid & 15, strip = ptid >> 4;               // 4 channels x kStripPx consecutive pixels
-    const int b0 = strip * kStripPx;
-    auto ld = [&](const uint8_t* rowp, float2 (&d)[2]) {
-      uint2 raw = *(const uint2*)rowp;
-      if (RELU_IN) {
-        const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
-        __nv_bfloat162* hb = (__nv_bfloat162*)&raw;
-        hb[0] = __hmax2(hb[0], z2);
-        hb[1] = __hmax2(hb[1], z2);
-      }
-      d[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
-      d[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
-    };
+    // This CTA's 80 rows are four padded image rows of 20 pixels.  A thread owns 4 channels x (2 image rows x 5 columns):
+    // it walks the four input rows of its 4 x 7 halo once, every loaded pixel feeds up to six outputs (28 window loads
+    // and unpacks per 10 outputs; the earlier one-row strips needed 42), and each output still accumulates its nine
+    // taps top row first, left to right -- the order of depthwise3x3_pipe_kernel, so the results are bit-identical.
+    // (Diagnostic builds: the producers' shared-memory loads and stores are free, their INSTRUCTIONS are what slows the
+    // kernel -- without the depthwise math it is 22 % faster, without the loads or without the stores not at all.)
+    const int ptid = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..127
+    const int c4 = ptid & 15, sp = ptid >> 4;                  // channel group; strip 0..7
+    const int rp = sp >> 2, cs = sp & 3;                       // image-row pair 0..1, column strip (columns 5 cs .. 5 cs + 4)
+    const int wbase = (2 * rp) * kPitch + kColsPerStrip * cs;  // window row of this thread's halo corner (input row -1, column -1)
     const uint32_t total_kb = (uint32_t)my_items * kNumKb;
-    // raw (bf16-pair) window loads; unpacked on use, so a row fetched one output ahead costs two registers, not four
+#ifdef BQ_SM_DIAG_NOLDS         // TIMING DIAGNOSTIC ONLY (wrong results): the producers do not read the window
+    auto ldraw = [&](const uint8_t* rowp) { return make_uint2((uint32_t)(size_t)rowp * 2654435761u, (uint32_t)(size_t)rowp); };
+#else
     auto ldraw = [&](const uint8_t* rowp) { return *(const uint2*)rowp; };
+#endif
     auto unpack = [&](uint2 raw, float2 (&d)[2]) {
       if (RELU_IN) {
         const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -601,24 +594,20 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       d[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
       d[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
     };
-    auto load_w = [&](int kb, float2 (&w)[9][2]) {
+    for (uint32_t q = 0; q < total_kb; ++q) {
+      const int kb = (int)(q % kNumKb);
+      const int is = (int)(q % kInStages), bs = (int)(q % kBStages);
+      const uint32_t iph = (q / kInStages) & 1u, bph = (q / kBStages) & 1u;
       const int c = kb * 64 + c4 * 4;
+      const bool live = c < kC + 8;                            // the last k-block feeds 2 k-steps (channels 704..735)
+      float2 w[9][2];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < 9; ++t) {                            // requested ahead of the two waits below
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < kC) wv = __ldg((const float4*)(p.dw + (size_t)t * kC + c));
         w[t][0] = make_float2(wv.x, wv.y);
         w[t][1] = make_float2(wv.z, wv.w);
       }
-    };
-    float2 w[9][2];
-    if (BQ_SM_SWPIPE && total_kb) load_w(0, w);
-    for (uint32_t q = 0; q < total_kb; ++q) {
-      const int kb = (int)(q % kNumKb);
-      const int is = (int)(q % kInStages), bs = (int)(q % kBStages);
-      const uint32_t iph = (q / kInStages) & 1u, bph = (q / kBStages) & 1u;
-      const bool live = kb * 64 + c4 * 4 < kC + 8;             // the last k-block feeds 2 k-steps (channels 704..735)
-      if (!BQ_SM_SWPIPE) load_w(kb, w);
       mbar_wait(in_full(is), iph);
       mbar_wait(b_empty(bs), bph ^ 1u);
 #ifdef BQ_SM_DIAG_NOPROD        // TIMING DIAGNOSTIC ONLY: producers skip the depthwise math
@@ -626,51 +615,47 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
 #else
       if (live) {
 #endif
-        // window row of output pixel o, tap (dy, dx): o + 21 + dy*20 + dx  ->  top o+{0,1,2}, mid o+{20,21,22}, bottom o+{40,41,42}
-        const uint8_t* win = smem_gen + kOffIn + is * kWinBytes + (size_t)b0 * 128 + c4 * 8;
+        // window row of input (iy, ix) of this thread's halo: wbase + iy * 20 + ix   (the window starts 21 rows before the CTA's first row)
+        const uint8_t* win = smem_gen + kOffIn + is * kWinBytes + (size_t)wbase * 128 + c4 * 8;
         uint8_t* bdst = smem_gen + kOffB + bs * kBBytes;
-        float2 tp[3][2], md[3][2], bt[3][2];
-        {
-          const uint2 r0 = ldraw(win), r1 = ldraw(win + 128), r2 = ldraw(win + 20 * 128), r3 = ldraw(win + 21 * 128);
-          const uint2 r4 = ldraw(win + 40 * 128), r5 = ldraw(win + 41 * 128);
-          unpack(r0, tp[0]); unpack(r1, tp[1]); unpack(r2, md[0]); unpack(r3, md[1]); unpack(r4, bt[0]); unpack(r5, bt[1]);
-        }
-        uint2 nt = ldraw(win + 2 * 128), nm = ldraw(win + 22 * 128), nb2 = ldraw(win + 42 * 128);
+        float2 acc[2][kColsPerStrip][2];
 #pragma unroll
-        for (int i = 0; i < kStripPx; ++i) {
-          const int i0 = i % 3, i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-          unpack(nt, tp[i2]); unpack(nm, md[i2]); unpack(nb2, bt[i2]);
-          if (BQ_SM_SWPIPE && i < kStripPx - 1) {       // the rows of the NEXT output are requested before this output's math (and before its store:
-                             // the compiler will not hoist a shared load above a shared store it cannot disambiguate)
-            nt = ldraw(win + (size_t)(i + 3) * 128);
-            nm = ldraw(win + (size_t)(i + 23) * 128);
-            nb2 = ldraw(win + (size_t)(i + 43) * 128);
+        for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+          for (int cx = 0; cx < kColsPerStrip; ++cx) acc[ry][cx][0] = acc[ry][cx][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int iy = 0; iy < 4; ++iy) {
+          float2 row[kColsPerStrip + 2][2];
+#pragma unroll
+          for (int ix = 0; ix < kColsPerStrip + 2; ++ix) unpack(ldraw(win + (size_t)(iy * kPitch + ix) * 128), row[ix]);
+#pragma unroll
+          for (int ry = 0; ry < 2; ++ry) {
+            const int ky = iy - ry;                            // this input row is filter row ky of output row ry
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int cx = 0; cx < kColsPerStrip; ++cx)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                acc[ry][cx][0] = __ffma2_rn(row[cx + kx][0], w[ky * 3 + kx][0], acc[ry][cx][0]);
+                acc[ry][cx][1] = __ffma2_rn(row[cx + kx][1], w[ky * 3 + kx][1], acc[ry][cx][1]);
+              }
           }
-          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-          a0 = __ffma2_rn(tp[i0][0], w[0][0], a0); a1 = __ffma2_rn(tp[i0][1], w[0][1], a1);
-          a0 = __ffma2_rn(tp[i1][0], w[1][0], a0); a1 = __ffma2_rn(tp[i1][1], w[1][1], a1);
-          a0 = __ffma2_rn(tp[i2][0], w[2][0], a0); a1 = __ffma2_rn(tp[i2][1], w[2][1], a1);
-          a0 = __ffma2_rn(md[i0][0], w[3][0], a0); a1 = __ffma2_rn(md[i0][1], w[3][1], a1);
-          a0 = __ffma2_rn(md[i1][0], w[4][0], a0); a1 = __ffma2_rn(md[i1][1], w[4][1], a1);
-          a0 = __ffma2_rn(md[i2][0], w[5][0], a0); a1 = __ffma2_rn(md[i2][1], w[5][1], a1);
-          a0 = __ffma2_rn(bt[i0][0], w[6][0], a0); a1 = __ffma2_rn(bt[i0][1], w[6][1], a1);
-          a0 = __ffma2_rn(bt[i1][0], w[7][0], a0); a1 = __ffma2_rn(bt[i1][1], w[7][1], a1);
-          a0 = __ffma2_rn(bt[i2][0], w[8][0], a0); a1 = __ffma2_rn(bt[i2][1], w[8][1], a1);
-          if (!BQ_SM_SWPIPE && i < kStripPx - 1) {
-            nt = ldraw(win + (size_t)(i + 3) * 128);
-            nm = ldraw(win + (size_t)(i + 23) * 128);
-            nb2 = ldraw(win + (size_t)(i + 43) * 128);
-          }
-          const int pr = b0 + i;
-          uint2 o;
-          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-          ob[0] = __floats2bfloat162_rn(a0.x, a0.y);
-          ob[1] = __floats2bfloat162_rn(a1.x, a1.y);
-          *(uint2*)(bdst + (size_t)pr * 128 + (((c4 >> 1) ^ (pr & 7)) << 4) + (c4 & 1) * 8) = o;
         }
+#pragma unroll
+        for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+          for (int cx = 0; cx < kColsPerStrip; ++cx) {
+            const int pr = (2 * rp + ry) * kPitch + kColsPerStrip * cs + cx;   // row of the depthwise stage (this CTA's pixel)
+            uint2 o;
+            __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+            ob[0] = __floats2bfloat162_rn(acc[ry][cx][0].x, acc[ry][cx][0].y);
+            ob[1] = __floats2bfloat162_rn(acc[ry][cx][1].x, acc[ry][cx][1].y);
+#ifdef BQ_SM_DIAG_NOSTS         // TIMING DIAGNOSTIC ONLY (wrong results): the producers do not write the depthwise stage
+            if (o.x == 0x12345678u && o.y == 0x9abcdef0u)
+#endif
+            *(uint2*)(bdst + (size_t)pr * 128 + (((c4 >> 1) ^ (pr & 7)) << 4) + (c4 & 1) * 8) = o;
+          }
       }
-      // the next k-block's taps are requested now: their L2 latency hides behind the fence, the arrives and the next waits
-      if (BQ_SM_SWPIPE && q + 1 < total_kb) load_w((int)((q + 1) % kNumKb), w);
       fence_async_smem();           // generic smem writes -> async proxy (tensor core), and window reads -> next TMA fill
       __syncwarp();
       if (lane == 0) {

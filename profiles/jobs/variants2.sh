@@ -1,5 +1,5 @@
 cp biscuit_b200/libbiscuit_b200.so /tmp/lib_default.so
-for f in profiles/variants/lib_e*.so; do
+for f in profiles/variants/lib_g*.so; do
   v=$(basename $f .so)
   cp $f biscuit_b200/libbiscuit_b200.so
   timeout 200 python bench.py --tiles 4096 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2> /tmp/err_$v.log | python -c "
@@ -10,7 +10,7 @@ print('$v', 'tiles/s %.0f' % d['value'], ' '.join('%s=%.1f' % (n, k[n]['ms']) fo
 done
 cp /tmp/lib_default.so biscuit_b200/libbiscuit_b200.so
 # second pass in the opposite order (box drift)
-for f in $(ls -r profiles/variants/lib_e*.so); do
+for f in $(ls -r profiles/variants/lib_g*.so); do
   v=$(basename $f .so)
   cp $f biscuit_b200/libbiscuit_b200.so
   timeout 200 python bench.py --tiles 4096 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2> /tmp/err_$v.log | python -c "
