@@ -154,6 +154,13 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
                : "r"(addr)
                : "memory");
 }
+// lo += bf16(pair.lo), hi += bf16(pair.hi) in fp32, round to nearest: the mixed-precision add (FHADD.BF16 with an .H0 / .H1
+// operand selector) reads the packed halves directly -- one instruction per element instead of unpack + add
+__device__ __forceinline__ void add_bf16x2_to_f32(float& lo, float& hi, uint32_t pair) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.rn.f32.bf16 %0, l, %0;\n\tadd.rn.f32.bf16 %1, h, %1;\n\t}"
+      : "+f"(lo), "+f"(hi)
+      : "r"(pair));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
   uint32_t r;
   if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -469,8 +476,7 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
                 const uint32_t qq[4] = {q0, q1, q2, q3};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  f[2 * k] = __fadd_rn(f[2 * k], __uint_as_float(qq[k] << 16));
-                  f[2 * k + 1] = __fadd_rn(f[2 * k + 1], __uint_as_float(qq[k] & 0xFFFF0000u));
+                  add_bf16x2_to_f32(f[2 * k], f[2 * k + 1], qq[k]);
                 }
               }
 #pragma unroll
