@@ -59,9 +59,12 @@ def delong_roc_variance(ground_truth, predictions, ctx=None):
 
 
 def delong_roc_test(ground_truth, predictions_one, predictions_two, ctx=None):
-    """log10(p-value) of the hypothesis that the two ROC AUCs differ (reference delong.py:110-123): a [[...]] 1 x 1 array,
-    as `calc_pvalue` returns it."""
-    p = _Placements(ground_truth, np.vstack((predictions_one, predictions_two)), ctx=ctx)
-    contrast = np.array([[1, -1]])
-    z = np.abs(np.diff(p.aucs)) / np.sqrt(np.dot(np.dot(contrast, p.covariance()), contrast.T))
-    return np.log10(2) + scipy.stats.norm.logsf(z, loc=0, scale=1) / np.log(10)
+    """log10(p-value) of the hypothesis that the two ROC AUCs differ (reference delong.py:76-123), returned as the 1 x 1
+    array the reference returns.  Two-sided z test on the AUC difference with the DeLong covariance S of the pair:
+    var = [1, -1] S [1, -1]^T, evaluated in the order of the reference's two dot products so the float64 result is the same."""
+    placements = _Placements(ground_truth, np.vstack((predictions_one, predictions_two)), ctx=ctx)
+    cov = np.asarray(placements.covariance(), dtype=np.float64)
+    var_of_difference = (cov[0, 0] - cov[1, 0]) - (cov[0, 1] - cov[1, 1])
+    z = np.abs(placements.aucs[1] - placements.aucs[0]) / np.sqrt(var_of_difference)
+    log10_p = np.log10(2) + scipy.stats.norm.logsf(z, loc=0, scale=1) / np.log(10)
+    return np.array([[log10_p]])

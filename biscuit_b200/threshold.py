@@ -818,33 +818,32 @@ _CV_COLUMNS = ("y_true", "y_pred", "uncertainty", "slide", "patient")
 
 
 def _from_cv(dfs, detect_fn, kwargs, require_patient=True, columns_of=lambda df: df.columns):
-    required = ("y_true", "y_pred", "uncertainty", "slide", "patient") if require_patient else \
-               ("y_true", "y_pred", "uncertainty", "slide")
-    skip_tile = "tile_uq_thresh" in kwargs and kwargs["tile_uq_thresh"] is None     # :513-516
-    skip_slide = "slide_uq_thresh" in kwargs and kwargs["slide_uq_thresh"] is None
-    k_tile, k_slide, k_tile_pred, k_slide_pred = [], [], [], []
+    """Fold pass + reduction of the reference's from_cv (threshold.py:478-557): every fold table is validated and run
+    through `detect_fn`; folds without both UQ thresholds drop out (:526-528); the survivors reduce to
+    min(tile_uq), max(slide_uq), mean(tile_pred), mean(slide_pred) (:544-557).  The two `*_uq_thresh=None` keywords
+    switch a UQ reduction off and leave an empty list in its place, as the reference does (:513-516)."""
+    required = ("y_true", "y_pred", "uncertainty", "slide") + (("patient",) if require_patient else ())
+    kept = []
     for idx, df in enumerate(dfs):
         log.debug(f"Detecting thresholds from fold {idx}")
-        if not all(col in columns_of(df) for col in required):        # :520-524
-            raise ValueError(f"DataFrame missing columns, expected {required}, got: "
-                             f"{', '.join(list(columns_of(df)))}")
-        thresholds, _ = detect_fn(df, **kwargs)                       # :525
-        if thresholds["tile_uq"] is None or thresholds["slide_uq"] is None:   # :526-528
+        present = list(columns_of(df))
+        if any(col not in present for col in required):
+            raise ValueError(f"DataFrame missing columns, expected {required}, got: {', '.join(present)}")
+        fold, _ = detect_fn(df, **kwargs)
+        if fold["tile_uq"] is None or fold["slide_uq"] is None:
             log.debug(f"Skipping CV #{idx}, unable to detect threshold")
             continue
-        k_tile_pred.append(thresholds["tile_pred"])
-        k_slide_pred.append(thresholds["slide_pred"])
-        if not skip_tile:
-            k_tile.append(thresholds["tile_uq"])
-        if not skip_slide:
-            k_slide.append(thresholds["slide_uq"])
-    if not skip_tile and not len(k_tile):                             # :539-542
-        raise errors.ThresholdError("Unable to detect tile UQ threshold.")
-    if not skip_slide and not len(k_slide):
-        raise errors.ThresholdError("Unable to detect slide UQ threshold.")
-    return {                                                          # :544-557
-        "tile_uq": np.min(k_tile) if not skip_tile else k_tile,
-        "slide_uq": np.max(k_slide) if not skip_slide else k_slide,
-        "tile_pred": np.mean(k_tile_pred),
-        "slide_pred": np.mean(k_slide_pred),
-    }
+        kept.append(fold)
+    reducers = {"tile_uq": ("tile", np.min), "slide_uq": ("slide", np.max)}
+    out = {}
+    for key, (what, reduce_fn) in reducers.items():
+        switched_off = kwargs.get(f"{key}_thresh", 0) is None and f"{key}_thresh" in kwargs
+        if switched_off:
+            out[key] = []
+        elif not kept:
+            raise errors.ThresholdError(f"Unable to detect {what} UQ threshold.")
+        else:
+            out[key] = reduce_fn([fold[key] for fold in kept])
+    for key in ("tile_pred", "slide_pred"):
+        out[key] = np.mean([fold[key] for fold in kept])
+    return out
