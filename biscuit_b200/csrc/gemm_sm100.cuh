@@ -178,6 +178,49 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of SWIZZLE bytes, 8-row groups.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1
 //   | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+// ---- accumulator-fragment epilogue helpers (fused sepconv kernels: TMEM lane = output channel) ----
+// 16 TMEM lanes x 256 bits: thread t gets (lane t/4, columns 2(t%4), 2(t%4)+1) in r0, r1 and (lane t/4 + 8, same columns) in
+// r2, r3 -- the m16n8 accumulator-fragment layout, repeated along the columns for .x4 (registers 4i.. = columns 8i..).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+// four 8x8 b16 matrices, transposed on the way to / from shared memory: thread i supplies the address of row i % 8 of
+// matrix i / 8; register k of thread t holds elements (row t/4, columns 2(t%4), 2(t%4)+1) of matrix k BEFORE the transpose
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+// lo += bf16(pair.lo), hi += bf16(pair.hi) in fp32, round to nearest: the mixed-precision add (FHADD.BF16 with an .H0 / .H1
+// operand selector) reads the packed halves directly -- one instruction per element instead of unpack + add
+__device__ __forceinline__ void add_bf16x2_to_f32(float& lo, float& hi, uint32_t pair) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.rn.f32.bf16 %0, l, %0;\n\tadd.rn.f32.bf16 %1, h, %1;\n\t}"
+      : "+f"(lo), "+f"(hi)
+      : "r"(pair));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
+  uint32_t r;
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 template <int SWIZZLE_BYTES>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2ull : (SWIZZLE_BYTES == 64 ? 4ull : 6ull);

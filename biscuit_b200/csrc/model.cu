@@ -482,7 +482,7 @@ int build_plan(bq_model* m) {
   // one SeparableConv2D (+BN, optional ReLU / residual): fused kernel for 728->728, otherwise depthwise + GEMM
   auto add_sep = [&](const bf16* in, bf16* dw_tmp, int h, int cin, int relu_in, const SepWeights& sw, bf16* out, int relu_out,
                      const bf16* resid, int stage, const char* tag, int in_pitch = 0) -> int {
-    if (!in_pitch && !m->use_simt && !resid && cin % 64 == 0 && cin <= 256 && sw.pw.cout <= 256 && sw.pw.cout % 64 == 0) {
+    if (!in_pitch && !m->use_simt && !resid && cin % 64 == 0 && cin <= 256 && (sw.pw.cout == 128 || sw.pw.cout == 256)) {
       Op op; op.kind = OP_SEP2D; op.stage = stage;
       if (tag) op.tag = tag;
       op.in = in; op.out = out; op.H = h; op.W = h; op.C = cin; op.Ho = h; op.Wo = h; op.Cout = sw.pw.cout;
@@ -492,7 +492,8 @@ int build_plan(bq_model* m) {
       int r;
       if ((r = make_tmap_nhwc(ctx, &op.ta, in, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)cin, bq::sep2d::kHH, bq::sep2d::kHW, 64, false))) return r;
       if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, (uint64_t)sw.pw.cout, (uint64_t)cin, (uint64_t)cin, (uint32_t)sw.pw.cout, 64))) return r;
-      if ((r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)sw.pw.cout, bq::sep2d::kPH, bq::sep2d::kPW, 64, true))) return r;
+      // one box per epilogue warp and step: 32 channels x 16 columns x 2 patch rows, SWIZZLE_64B staging tiles
+      if ((r = make_tmap_nhwc(ctx, &op.tc, out, (uint64_t)B, (uint64_t)h, (uint64_t)h, (uint64_t)sw.pw.cout, 2, bq::sep2d::kPW, 32, false, true))) return r;
       m->plan.push_back(op);
       return BQ_OK;
     }

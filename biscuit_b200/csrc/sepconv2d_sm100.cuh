@@ -3,14 +3,20 @@
 //
 //     out[8x16 px, N] = epilogue( depthwise3x3(relu?(x))[8x16 px, K] @ Wpw[N, K]^T )
 //
-// A work item is an 8 x 16 pixel patch of one image (= the 128 rows of a UMMA M tile).  Per 64-channel k-block:
+// A work item is an 8 x 16 pixel patch of one image.  The GEMM is issued TRANSPOSED (as in sepmid_sm100.cuh): the weights
+// are the M-side operand and the 128 pixels the N-side operand, D^T[128 ch, 128 px] += W[128, 64] * dw[128, 64]^T per
+// channel tile, so a TMEM lane is an output CHANNEL: the epilogue keeps its BatchNorm constants in four registers and
+// transposes with stmatrix instead of fetching two constants per output from shared memory (these layers were
+// epilogue-bound: 4.1 -> 2.6 instructions per output).  Per 64-channel k-block:
 //   warp 0      one 4-D TMA load of the (8+2) x (16+2) x 64 halo patch (zero fill outside the image = 'same' padding) and
 //               one TMA load of the [N x 64] pointwise-weight k-block;
 //   warps 6-13  depthwise producers: thread = (4 channels, one patch column), vertical 3x3 register window walking down
 //               the 8 rows (3 LDS.64 + 18 FFMA2 per 4 outputs, weights in registers) -> bf16 -> the 128B-swizzled A stage;
-//   warp 1      tcgen05.mma 128 x N x 16 (x4 per k-block), accumulators double-buffered in TMEM;
-//   warps 2-5   epilogue: tcgen05.ld -> BN scale/shift -> ReLU -> bf16 -> swizzled staging -> 4-D TMA store (image border
-//               clipped by the TMA unit).
+//   warp 1      tcgen05.mma 128 x 128 x 16 (x4 per k-block and channel tile), accumulators double-buffered in TMEM;
+//   warps 2-9   epilogue, eight independent warp pipelines (no block barrier): warp = (32 channels, 64 pixels);
+//               tcgen05.ld.16x256b accumulator fragments -> BN scale/shift (ReLU fused into the bf16 pack) ->
+//               stmatrix.trans into the warp's [32 px][32 ch] staging tile -> 4-D TMA store of two patch rows (image
+//               border clipped by the TMA unit).
 // The depthwise output never touches L2/HBM (saves one tensor write + one tensor read per layer) and its CUDA-core work
 // runs under the TMA / tensor-core work of the same kernel.
 #pragma once
@@ -26,19 +32,17 @@ constexpr int kPH = 8, kPW = 16;                               // output patch (
 constexpr int kHH = kPH + 2, kHW = kPW + 2;                    // halo patch 10 x 18
 constexpr int kPatchBytes = 23 * 1024;                         // 10*18*128 = 23,040 B, padded to a multiple of 1024
 constexpr int kABytes = 128 * 128;
-constexpr int kOutBytes = 128 * 128;
+constexpr int kOutTile = 32 * 64;                              // one epilogue warp's staging tile: [32 px][32 ch] bf16, SWIZZLE_64B
+constexpr int kOutBufs = 2;                                    // rotating per warp: one store may still be reading (N = 256 leaves no room for a third)
+constexpr int kOutBytes = 8 * kOutBufs * kOutTile;             // eight epilogue warps
 constexpr int kMaxPStages = 5, kAStages = 2, kBStages = 2;
 constexpr int kOffPatch = 0;
-// runtime layout (all offsets multiples of 1024): [patch x P][A x 2][B x 2 (N*128 B each)][out x 2][scale/shift][barriers]
-// P = 4 halo-patch stages for N = 256, 5 for N <= 128: the kernel is HBM-latency bound, so every spare KB is patch in flight
+// runtime layout (all offsets multiples of 1024): [patch x P][A x 2][B x 2 (N*128 B each)][out][scale/shift][barriers]
 __host__ __device__ inline int patch_stages(int N) { (void)N; return 4; }
-// N == 128 ("dual" epilogue): the two 64-column halves of an item are drained CONCURRENTLY by the two groups of four
-// epilogue warps, each with its own pair of staging buffers, its own 128-thread barrier and its own TMA stores
-__host__ __device__ inline int out_bufs(int N) { return N == 128 ? 4 : 2; }
 __host__ __device__ inline int off_a(int N) { return patch_stages(N) * kPatchBytes; }
 __host__ __device__ inline int off_b(int N) { return off_a(N) + kAStages * kABytes; }
 __host__ __device__ inline int off_out(int N) { return off_b(N) + kBStages * N * 128; }
-__host__ __device__ inline int off_scale(int N) { return off_out(N) + out_bufs(N) * kOutBytes; }
+__host__ __device__ inline int off_scale(int N) { return off_out(N) + kOutBytes; }
 __host__ __device__ inline int off_bar(int N) { return off_scale(N) + 2 * 256 * 4; }
 __host__ __device__ inline int smem_bytes(int N) { return off_bar(N) + 512 + 1024; }
 constexpr int kThreads = 576;                                 // warp 0 TMA, 1 MMA, 2-9 epilogue (8), 10-17 producers (8)
@@ -46,7 +50,7 @@ constexpr int kProducerWarps = 8;
 
 struct Sep2dParams {
   int n_img, H, W;          // images in this launch, map size
-  int K, N;                 // input / output channels (K % 64 == 0, K <= 256; N % 16 == 0, N <= 256)
+  int K, N;                 // input / output channels (K % 64 == 0, K <= 256; N = 128 or 256)
   int relu_in, relu_out;
   const float* dw;          // [9][K]
   const float* scale;       // [N]
@@ -57,7 +61,7 @@ template <bool RELU_IN>
 __global__ void __launch_bounds__(kThreads, 1)
 sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H, n] box [64, 18, 10, 1], no swizzle*/,
                        const __grid_constant__ CUtensorMap tmap_w /*2-D [N, K] box [64 x N], SW128*/,
-                       const __grid_constant__ CUtensorMap tmap_out /*4-D [N, W, H, n] box [64, 16, 8, 1], SW128*/,
+                       const __grid_constant__ CUtensorMap tmap_out /*4-D [N, W, H, n] box [32, 16, 2, 1], SW64*/,
                        const Sep2dParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -142,26 +146,30 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
   } else if (warp == 1) {
     // ===================== MMA issuer: converged warp, one elected lane issues (see elect_one()) =====================
     {
-      const uint32_t idesc = make_idesc(128, p.N);
+      const uint32_t idesc = make_idesc(128, 128);   // M = 128 output channels (weights), N = the patch's 128 pixels
+      const int n_ct = p.N >> 7;
       int as = 0; uint32_t aph = 0;                // A / B rings advance together (one step per k-block)
       int cs = 0; uint32_t cph = 0;                // accumulator stage per item
       int gk = 0;                                  // k-blocks issued so far (resident weights: only the first two wait for B)
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         mbar_wait(acc_empty(cs), cph ^ 1u);
-        const uint32_t d = tmem_base + (uint32_t)(cs * 256);
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(a_full(as), aph);
           if (!b_resident || gk < kBStages) mbar_wait(b_full(as), aph);
           ++gk;
           tc_fence_after();
-          const uint64_t da = make_smem_desc<128>(smem_base + kOffA + as * kABytes);
-          const uint64_t db = make_smem_desc<128>(smem_base + kOffB + as * kBBytes);
+          const uint64_t dpx = make_smem_desc<128>(smem_base + kOffA + as * kABytes);      // depthwise stage: [128 px][64 k]
+          const uint64_t dw0 = make_smem_desc<128>(smem_base + kOffB + as * kBBytes);      // weights: [N ch][64 k]
           if (elect_one()) {
-            umma_bf16(d, da, db, idesc, kb ? 1u : 0u);
-            umma_bf16(d, da + 2u, db + 2u, idesc, 1u);
-            umma_bf16(d, da + 4u, db + 4u, idesc, 1u);
-            umma_bf16(d, da + 6u, db + 6u, idesc, 1u);
+            for (int ct = 0; ct < n_ct; ++ct) {
+              const uint64_t dw = dw0 + (uint64_t)(ct * ((128 * 128) >> 4));
+              const uint32_t d = tmem_base + (uint32_t)(cs * 256 + ct * 128);
+              umma_bf16(d, dw, dpx, idesc, kb ? 1u : 0u);
+              umma_bf16(d, dw + 2u, dpx + 2u, idesc, 1u);
+              umma_bf16(d, dw + 4u, dpx + 4u, idesc, 1u);
+              umma_bf16(d, dw + 6u, dpx + 6u, idesc, 1u);
+            }
             umma_commit(a_empty(as));
             if (!b_resident) umma_commit(b_empty(as));
             if (kb == num_kb - 1) umma_commit(acc_full(cs));
@@ -173,127 +181,84 @@ sepconv2d_fused_kernel(const __grid_constant__ CUtensorMap tmap_x /*4-D [K, W, H
       }
     }
   } else if (warp < 10) {
-    // ===================== epilogue: 8 warps = (TMEM lane quadrant, 32-column half of each 64-column chunk) =====================
+    // ===================== epilogue: eight independent warp pipelines =====================
+    // warp = (TMEM lane quadrant: 32 channels of a channel tile, pixel half: patch rows 4 hh .. 4 hh + 3).  A step is
+    // 32 pixels (two patch rows) x 32 channels: thread t holds channels t/4 + {0, 8, 16, 24} and the pixel pairs 2(t%4) of
+    // every 8-pixel block (accumulator-fragment layout), so the BatchNorm constants are four scale/shift pairs per
+    // thread and channel tile, a pixel pair packs into one bf16x2 register (cvt.rn.relu fuses the ReLU), and one
+    // stmatrix.x4.trans writes an [8 px][32 ch] block of the staging tile (64-byte rows, SWIZZLE_64B).
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = quad * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
-    int cs = 0; uint32_t cph = 0, cc = 0;
-    if (p.N == 128) {
-      // ---- dual epilogue: warps 2-5 own columns 0..63, warps 6-9 columns 64..127 of every item.  These layers have
-      // one or two k-blocks per item, the epilogue is their critical role (ncu: its warps busy 83 % of the time), and
-      // draining the halves one after the other cost four 256-thread barriers per item.
-      const bool hleader = (quad == 0 && lane == 0);              // warp 4 (half 0) / warp 8 (half 1)... quad 0 of each half
-      uint32_t item = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item) {
-        const int img = it / per_img, t = it - img * per_img;
-        const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
-        const uint32_t buf = (item & 1u) * 2u + (uint32_t)half;
-        uint8_t* st = smem_gen + kOffOut + buf * kOutBytes;
-        mbar_wait(acc_full(cs), cph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * 256 + half * 64);
-        if (hleader) tma_store_wait_read1();                      // this half's store of two items ago has drained
-        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-        for (int g2 = 0; g2 < 2; ++g2) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + (uint32_t)(g2 * 32), v);
-          tmem_ld_wait();
-          if (g2 == 1) {                                          // accumulators fully read -> next item may start
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(cs));
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = half * 64 + g2 * 32 + g * 8;
-            const float4 s0 = *(const float4*)(s_scale + n), s1 = *(const float4*)(s_scale + n + 4);
-            const float4 h0 = *(const float4*)(s_shift + n), h1 = *(const float4*)(s_shift + n + 4);
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
-              if (p.relu_out) f[j] = fmaxf(f[j], 0.f);
-            }
-            uint4 o;
-            __nv_bfloat162* ob = (__nv_bfloat162*)&o;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            const int chunk16 = g2 * 4 + g;
-            *(uint4*)(st + (size_t)row * 128 + ((chunk16 ^ (row & 7)) << 4)) = o;
-          }
-        }
-        fence_async_smem();
-        if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (hleader) {
-          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                       ::"l"((uint64_t)&tmap_out), "r"(smem_base + kOffOut + buf * kOutBytes), "r"(half * 64), "r"(x0), "r"(y0), "r"(img)
-                       : "memory");
-          tma_store_commit();
-        }
-        if (++cs == 2) { cs = 0; cph ^= 1u; }
-      }
-      if (hleader) tma_store_wait_all();
-    } else
+    const int hh = (warp - 2) >> 2;
+    const int w8 = warp - 2;
+    const int n_ct = p.N >> 7;
+    const uint32_t my_out = smem_base + kOffOut + (uint32_t)(w8 * kOutBufs * kOutTile);
+    const int mrow = lane & 7, mmat = lane >> 3;                  // this lane's row-address duty for stmatrix
+    int cs = 0; uint32_t cph = 0;
+    uint32_t g = 0;                                               // running step counter of this warp
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int img = it / per_img, t = it - img * per_img;
       const int y0 = (t / px_tiles) * kPH, x0 = (t % px_tiles) * kPW;
       mbar_wait(acc_full(cs), cph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * 256);
-      for (int c = 0; c < p.N; c += 64, ++cc) {
-        const uint32_t buf = cc & 1u;
-        uint8_t* st = smem_gen + kOffOut + buf * kOutBytes;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + (uint32_t)(c + half * 32), v);
-        tmem_ld_wait();
-        if (c + 64 >= p.N) {                                    // accumulators fully read -> next item may start
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty(cs));
+      for (int ct = 0; ct < n_ct; ++ct) {
+        float s4[4], h4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = ct * 128 + quad * 32 + (lane >> 2) + 8 * k;
+          s4[k] = s_scale[c];
+          h4[k] = s_shift[c];
         }
-        if (leader) tma_store_wait_read1();                     // the store that last used THIS staging buffer has drained
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t t_lo = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cs * 256 + ct * 128 + hh * 64);
+        const uint32_t t_hi = t_lo + (16u << 16);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = c + half * 32 + g * 8;
-          float f[8];
-          if (n < p.N) {
-            const float4 s0 = *(const float4*)(s_scale + n), s1 = *(const float4*)(s_scale + n + 4);
-            const float4 h0 = *(const float4*)(s_shift + n), h1 = *(const float4*)(s_shift + n + 4);
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __fadd_rn(__fmul_rn(__uint_as_float(v[g * 8 + j]), sc[j]), sh[j]);
-              if (p.relu_out) f[j] = fmaxf(f[j], 0.f);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        for (int s2 = 0; s2 < 2; ++s2, ++g) {
+          uint32_t lo[16], hi[16];
+          tmem_ld_16x256b_x4(t_lo + (uint32_t)(s2 * 32), lo);
+          tmem_ld_16x256b_x4(t_hi + (uint32_t)(s2 * 32), hi);
+          tmem_ld_wait();
+          if (ct == n_ct - 1 && s2 == 1) {                        // accumulators fully read -> the next item may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(cs));
           }
-          uint4 o;
-          __nv_bfloat162* ob = (__nv_bfloat162*)&o;
+          uint32_t pkv[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          const int chunk16 = half * 4 + g;
-          *(uint4*)(st + (size_t)row * 128 + ((chunk16 ^ (row & 7)) << 4)) = o;
-        }
-        fence_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader) {
-          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                       ::"l"((uint64_t)&tmap_out), "r"(smem_base + kOffOut + buf * kOutBytes), "r"(c), "r"(x0), "r"(y0), "r"(img)
-                       : "memory");
-          tma_store_commit();
+          for (int b = 0; b < 4; ++b) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              f[2 * k] = __fadd_rn(__fmul_rn(__uint_as_float(lo[4 * b + 2 * k]), s4[k]), h4[k]);
+              f[2 * k + 1] = __fadd_rn(__fmul_rn(__uint_as_float(lo[4 * b + 2 * k + 1]), s4[k]), h4[k]);
+              f[4 + 2 * k] = __fadd_rn(__fmul_rn(__uint_as_float(hi[4 * b + 2 * k]), s4[2 + k]), h4[2 + k]);
+              f[4 + 2 * k + 1] = __fadd_rn(__fmul_rn(__uint_as_float(hi[4 * b + 2 * k + 1]), s4[2 + k]), h4[2 + k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pkv[4 * b + k] = pack_bf16x2(f[2 * k], f[2 * k + 1], p.relu_out != 0);
+          }
+          const uint32_t stg = my_out + (g % kOutBufs) * kOutTile;
+          // buffer g % kOutBufs was last stored from kOutBufs steps ago: only now must that store have finished reading it
+          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kOutBufs - 1) : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int r = 8 * b + mrow;
+            stmatrix_x4_trans(stg + r * 64 + ((mmat ^ ((r >> 1) & 3)) << 4), pkv[4 * b], pkv[4 * b + 1], pkv[4 * b + 2], pkv[4 * b + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"((uint64_t)&tmap_out), "r"(stg), "r"(ct * 128 + quad * 32), "r"(x0), "r"(y0 + hh * 4 + s2 * 2), "r"(img)
+                         : "memory");
+            tma_store_commit();
+          }
+          __syncwarp();
         }
       }
       if (++cs == 2) { cs = 0; cph ^= 1u; }
     }
-    if (leader) tma_store_wait_all();
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
   } else {
     // ===================== depthwise producers =====================
     // Two groups of four warps take alternate k-blocks (group g owns A stage g); a thread = (4 channels, TWO adjacent
