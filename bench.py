@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--tiles", type=int, default=10000, help="tiles per slide (per GPU per step)")
     ap.add_argument("--slides", type=int, default=1, help="slides per GPU per step")
     ap.add_argument("--T", type=int, default=30)
-    ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--max-batch", type=int, default=503, help="micro-batch (biscuit_b200.uq.BENCH_MICRO_BATCH)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target size of the CPU-baseline sample")

@@ -267,10 +267,10 @@ def test_results_do_not_depend_on_micro_batch():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# The configuration bench.py times (max_batch = 512: CUDA-graph replay, batched fused head, full-size GEMM rings)
-# tied to the oracle
+# The configuration bench.py times (max_batch = biscuit_b200.uq.BENCH_MICRO_BATCH: CUDA-graph replay, batched fused
+# head, full-size GEMM rings) tied to the oracle
 # ----------------------------------------------------------------------------------------------------------------
-BENCH_BATCH = 512
+from biscuit_b200.uq import BENCH_MICRO_BATCH as BENCH_BATCH  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -282,7 +282,7 @@ def bench_iface(weights):
 
 
 def test_bench_micro_batch_bit_identical_to_small_batch(weights, bench_iface, iface):
-    """530 tiles at max_batch = 512 (one full graph-replayed micro-batch + a partial one, fused head launched on
+    """530 tiles at the bench micro-batch (one full graph-replayed micro-batch + a partial one, fused head launched on
     >= 592-tile... here 530-tile batches) and the same tiles at max_batch = 4 (the batch size the stage-wise oracle
     parity tests run at): bit-identical features / mean / std.  Transitively ties the bench configuration to the
     oracle."""
@@ -294,18 +294,18 @@ def test_bench_micro_batch_bit_identical_to_small_batch(weights, bench_iface, if
     small = iface.predict(t, T=T, seed=21, return_features=True)
     for a, b, name in zip(big, small, ("mean", "std", "features")):
         bad = np.nonzero(np.abs(a - b).reshape(n, -1).max(1) > 0)[0]
-        assert a.tobytes() == b.tobytes(), f"{name}: {len(bad)} tiles differ between max_batch 512 and 4, first {bad[:8]}"
+        assert a.tobytes() == b.tobytes(), f"{name}: {len(bad)} tiles differ between max_batch {BENCH_BATCH} and 4, first {bad[:8]}"
     # a second call replays the captured graph: still identical
     again = bench_iface.predict(t, T=T, seed=21, return_features=True)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(big, again))
 
 
 def test_oracle_parity_at_bench_micro_batch(weights, bench_iface, tiles):
-    """max_batch = 512: the six oracle tiles scattered over a 520-tile run (first / interior / last row of the full
-    micro-batch, and the partial second micro-batch) against the bf16-emulated oracle directly, own Philox stream
-    addressed by the GLOBAL tile index."""
-    n = 520
-    pos = [0, 63, 257, 511, 512, 519]
+    """The bench micro-batch: the six oracle tiles scattered over a run of one full micro-batch + 8 tiles (first /
+    interior / last row of the full micro-batch, and the partial second micro-batch) against the bf16-emulated oracle
+    directly, own Philox stream addressed by the GLOBAL tile index."""
+    n = BENCH_BATCH + 8
+    pos = [0, 63, 257, BENCH_BATCH - 1, BENCH_BATCH, n - 1]
     filler = synth.tiles_u8(16, seed=33, n_slides=2)
     allt = np.concatenate([filler] * (n // 16 + 1))[:n].copy()
     for k, p in enumerate(pos):
