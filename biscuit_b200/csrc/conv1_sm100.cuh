@@ -8,8 +8,8 @@
 //     the common term up front keeps the accumulators small: exactly 0 on a constant tile);
 //   * B holds the fp32 filter split into THREE bf16 terms  w = hi + mid + lo  (3 x 8 significand bits = fp32's 24) laid
 //     along K: the same A stage is multiplied with the hi, mid and lo rows in turn and all three accumulate into ONE fp32
-//     TMEM tile.  Every product is exact in fp32, so the accumulator holds the fp32 convolution of the raw pixels up to
-//     fp32 summation rounding;
+//     TMEM tile.  Every product is exact in fp32, so the accumulator holds the fp32 convolution of the mean-removed pixels up
+//     to fp32 summation rounding;
 //   * the standardisation is affine and the layer is bias-free and 'valid', so it moves behind the convolution together
 //     with the folded BatchNorm:  BN(conv(W, (x - m) / sd)) = conv(W, x - m0) * g + h,  g = scale / sd,
 //     h = shift - (m - m0) * sum(W) * g, computed per tile in fp64 by tile_stats_kernel; the epilogue is one FMA + ReLU.
@@ -41,11 +41,12 @@ constexpr int kItemsPerImg = (kPx + 127) / 128;                    // 174
 constexpr int kN = 32;                                             // output channels
 constexpr int kWRows = 96;                                         // hi | mid | lo rows of the weight tile
 constexpr int kABytes = 128 * 64;                                  // 128 rows x 32 bf16
-constexpr int kWBytes = kN * 64;                                   // 6 KB
+constexpr int kWBytes = kWRows * 64;                               // 6 KB (fits below kOffA)
 constexpr int kInBytes = 5 * kRowBytes + 32;                       // 5 rows + alignment slack -> round up to 16
 constexpr int kInSlots = (kInBytes + 15) / 16;                     // 284 uint4
 constexpr int kOffW = 0;
 constexpr int kOffA = 8192;                                        // 1024-aligned
+static_assert(kWBytes <= kOffA, "weight tile");
 constexpr int kInStages = 4;
 constexpr int kOffIn = kOffA + 2 * kABytes;
 constexpr int kOffOut = (kOffIn + kInStages * kInSlots * 16 + 1023) & ~1023;   // 4 epilogue warps x 2 x [32 px][64 B]
