@@ -57,3 +57,16 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_bench_micro_batch_fills_the_middle_flow_rounds():
+    """uq.BENCH_MICRO_BATCH is chosen so that the fused middle-flow kernel's work items (160 rows of the 400-row padded
+    image layout) divide evenly over the 74 CTA pairs of a 148-SM B200 (sepmid_sm100.cuh); it must also respect the
+    library's micro-batch cap."""
+    from biscuit_b200.uq import BENCH_MICRO_BATCH as B
+    src = open(os.path.join(ROOT, "biscuit_b200", "csrc", "sepmid_sm100.cuh")).read()
+    rows_per_image = int(re.search(r"kPitch = (\d+)", src).group(1)) ** 2
+    item = int(re.search(r"kItemPx = (\d+)", src).group(1))
+    assert (rows_per_image, item) == (400, 160)
+    items = -(-rows_per_image * B // item)
+    assert items % 74 == 0 and B <= 512
