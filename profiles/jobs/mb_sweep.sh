@@ -1,4 +1,4 @@
-for mb in 512 503 473 503 512; do
+for mb in 503 500 503 500; do
   timeout 200 python bench.py --steps 3 --warmup 3 --max-batch $mb --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels']
