@@ -555,10 +555,10 @@ int build_plan(bq_model* m) {
       int r;
       if ((r = make_tmap(ctx, &op.ta, P(src), rows, kC, kC, kWinRows, 64, true))) return r;
       if ((r = make_tmap(ctx, &op.tb, sw.pw.w.p, kC, kC, kC, 128, 64))) return r;
-      // 32-channel (64-byte) boxes: SWIZZLE_64B with the fragment epilogue (stmatrix rows), plain with the lane-per-channel one
-      if ((r = make_tmap(ctx, &op.tc, P(dst), rows, kC, kC, kMap, 32, !BQ_SM_EPI_V2))) return r;
+      // 32-channel (64-byte) boxes, SWIZZLE_64B: the fragment epilogue writes stmatrix rows
+      if ((r = make_tmap(ctx, &op.tc, P(dst), rows, kC, kC, kMap, 32))) return r;
       op.tr = op.tc;
-      if (res >= 0 && (r = make_tmap(ctx, &op.tr, P(res), rows, kC, kC, kStepPx, 32, !BQ_SM_EPI_V2))) return r;
+      if (res >= 0 && (r = make_tmap(ctx, &op.tr, P(res), rows, kC, kC, kStepPx, 32))) return r;
       m->plan.push_back(op);
       return BQ_OK;
     };

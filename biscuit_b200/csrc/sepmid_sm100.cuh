@@ -85,12 +85,6 @@ constexpr int kSmem = kOffBar + 512 + 1024;     // + slack for the 1024 B alignm
 // developer tunables (profiles/build_variants.py builds A/B copies of the library with -D overrides)
 constexpr int kProducerWarps = 4;               // 128 threads = 16 channel groups x (2 image-row pairs x 4 column strips)
 constexpr int kColsPerStrip = 5;                // 4 strips x 5 columns = the 20-pixel padded row
-#ifndef BQ_SM_EPI_V2
-#define BQ_SM_EPI_V2 1         // epilogue on accumulator fragments (tcgen05.ld.16x256b + stmatrix.trans) instead of one lane per channel
-#endif
-#ifndef BQ_SM_EARLY
-#define BQ_SM_EARLY 1          // epilogue hands a channel tile back before its first staging store
-#endif
 constexpr int kThreads = 32 * (3 + 8 + kProducerWarps);   // warp 0 weight TMA, 1 MMA, 2-9 epilogue, 10.. producers, last: window TMA (registers are granted per 4 warps: 19 cost as 20)
 constexpr int kEpiWarps = 8;
 constexpr int kSlackRows = 2 * kItemPx;         // rows allocated past the last image (the last item may overhang)
@@ -110,21 +104,6 @@ struct SepMidParams {
 // ptxas lowers them to MEMBAR.ALL.GPU on every producer thread and CCTL.IVALL (an L1 flush) on the waiting MMA thread,
 // per k-block -- measured 1.8x slower than the separate kernels.  Shared memory is not cached anywhere, the CTA-level
 // membar completes the stores before the arrive is sent, and the arrive reaches the leader strictly later.
-__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
 
 // Issue order inside MMA step t (shared by the TMA and the MMA warp): slot j -> channel tile, or -1.  Tile ct works on
 // stream position t - ct; the one group that STARTS an item (k-block 0: it must wait for the epilogue) is issued last so
@@ -292,19 +271,9 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
     const int quad = warp & 3;                        // TMEM lane quadrant -> channels quad*32 .. +31 of this CTA's 128
     const int hh = (warp - 2) >> 2;                   // pixel half: columns hh*80 .. +79
     const int w8 = warp - 2;
-    float sc[3], sh[3];
-    int chn[3];
-#pragma unroll
-    for (int ct = 0; ct < 3; ++ct) {
-      chn[ct] = ct * 256 + (int)rank * 128 + quad * 32 + lane;
-      const bool ok = chn[ct] < kC;
-      sc[ct] = ok ? __ldg(p.scale + chn[ct]) : 0.f;
-      sh[ct] = ok ? __ldg(p.shift + chn[ct]) : 0.f;
-    }
     const bool has_res = p.residual != nullptr;
     const uint32_t total_steps = (uint32_t)my_items * 6u;
     const uint32_t my_out = smem_base + kOffOut + w8 * (kEpiBufs * kOutTile);
-    uint8_t* my_out_gen = smem_gen + kOffOut + w8 * (kEpiBufs * kOutTile);
     auto step_coords = [&](uint32_t gg, int& row0, int& col0) {     // warp-local step index -> first row / first channel
       const uint32_t li2 = gg / 6u, r6 = gg % 6u;
       row0 = (cluster_id + (int)li2 * num_clusters) * kItemPx + hh * kCtaPx + (int)(r6 & 1u) * kStepPx;
@@ -328,59 +297,6 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
       for (int ct = 0; ct < 3; ++ct) {
         mbar_wait(acc_full(ct), (uint32_t)li & 1u);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * kItemPx + hh * kCtaPx);
-        uint32_t pk[20];
-        auto load40 = [&](uint32_t col, uint32_t (&v)[40]) {
-          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-          uint32_t (&v1)[8] = *reinterpret_cast<uint32_t (*)[8]>(&v[32]);
-          tmem_ld_32x32b_x32(t_addr + col, v0);
-          tmem_ld_32x32b_x8(t_addr + col + 32u, v1);
-          tmem_ld_wait();
-        };
-        auto finish = [&](const uint32_t (&v)[40], uint32_t gg) {          // -> pk[]: bf16 pairs (pixel j, j + 1)
-          const uint32_t e = gg % kEpiBufs;
-          const uint8_t* st = my_out_gen + e * kOutTile + lane * 2;
-          if (has_res) mbar_wait(res_full(w8, e), (gg / kEpiBufs) & 1u);
-#pragma unroll
-          for (int j = 0; j < 40; j += 2) {
-            float f0 = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), sc[ct]), sh[ct]);
-            float f1 = __fadd_rn(__fmul_rn(__uint_as_float(v[j + 1]), sc[ct]), sh[ct]);
-            if (has_res) {
-              f0 = __fadd_rn(f0, __bfloat162float(*(const bf16*)(st + j * 64)));
-              f1 = __fadd_rn(f1, __bfloat162float(*(const bf16*)(st + (j + 1) * 64)));
-            }
-            if (p.relu_out) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-            const __nv_bfloat162 b = __floats2bfloat162_rn(f0, f1);
-            pk[j >> 1] = *(const uint32_t*)&b;
-          }
-        };
-        auto store_step = [&](uint32_t gg) {
-          const uint32_t e = gg % kEpiBufs;
-          uint8_t* st = my_out_gen + e * kOutTile + lane * 2;
-#pragma unroll
-          for (int j = 0; j < 40; j += 2) {
-            *(uint16_t*)(st + j * 64) = (uint16_t)(pk[j >> 1] & 0xFFFFu);
-            *(uint16_t*)(st + (j + 1) * 64) = (uint16_t)(pk[j >> 1] >> 16);
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (elect_one()) {
-            int row0, col0;
-            step_coords(gg, row0, col0);
-            // one box of 19 valid pixels per image row; zero rows (y == 19), rows past the batch and channels >= 728 are skipped
-#pragma unroll
-            for (int r2 = 0; r2 < 2; ++r2) {
-              const int row = row0 + r2 * kPitch;
-              const int y = (row / kPitch) % kPitch;
-              if (y != kMap && row < p.n_rows && col0 < kC)
-                tma_store_2d(&tmap_out, my_out + e * kOutTile + r2 * kPitch * 64, col0, row);
-            }
-            tma_store_commit();
-            tma_store_wait_read1();                            // this warp's stores of step gg - 1 have drained buffer (gg + 2) % 3
-            if (has_res) prefetch_res(gg + 2);
-          }
-          __syncwarp();
-        };
 #ifdef BQ_SM_DIAG_NOEPI          // TIMING DIAGNOSTIC ONLY: the epilogue only hands the tile back
         if (true) {
           tc_fence_before();
@@ -389,8 +305,7 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           g += 2;
         } else
 #endif
-#if BQ_SM_EPI_V2
-        if (true) {
+        {
           // Fragment epilogue.  Thread t holds channels cq = t/4 + {0, 8, 16, 24} of the warp's 32 and pixel pairs
           // 2(t%4) of every 8-pixel block: BN constants are four per channel tile, a pixel pair packs into one bf16x2
           // register (cvt.rn.relu fuses the ReLU), and ONE stmatrix.x4.trans writes an [8 px][32 ch] block of the
@@ -481,29 +396,13 @@ sepconv_mid_kernel(const __grid_constant__ CUtensorMap tmap_in /*[rows, 728] box
           uint32_t lo[20], hi[20];
           load_step(0, lo, hi);
           finish2(lo, hi, g);
-          if (!BQ_SM_EARLY) store_step2(g);
           load_step(1, lo, hi);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
-          if (BQ_SM_EARLY) store_step2(g);
+          store_step2(g);                                      // (the channel tile was handed back before its first staging store)
           finish2(lo, hi, g + 1);
           store_step2(g + 1);
-          g += 2;
-        } else
-#endif
-        {
-          uint32_t v[40];
-          load40(0u, v);
-          finish(v, g);
-          if (!BQ_SM_EARLY) store_step(g);
-          load40((uint32_t)kStepPx, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (is_leader) mbar_arrive(acc_empty(ct)); else mbar_arrive_remote(acc_empty(ct), 0); }
-          if (BQ_SM_EARLY) store_step(g);
-          finish(v, g + 1);
-          store_step(g + 1);
           g += 2;
         }
       }
