@@ -150,3 +150,64 @@ def test_byte_collectives_single_process():
     assert t.shape[0] == 2 * 17
     yp, un, yt = bdist.unpack_tiles(bdist.all_gather_bytes(t, [t.shape[0]])[0], 2, np.float64)
     assert yp.tolist() == [.5, .25] and un.tolist() == [.1, .2] and yt.tolist() == [1, 0]
+
+
+# ---- property tests of the host-side exchange helpers (hypothesis): the N > 1 path must be lossless byte for byte ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=5000), min_size=0, max_size=80), st.integers(min_value=1, max_value=16))
+def test_shard_bounds_partition_any_cohort(counts, world):
+    """Any cohort (empty, fewer slides than ranks, empty slides) is split into `world` contiguous, slide-aligned,
+    ordered ranges that cover it exactly; with more ranks than slides the surplus ranks get empty shards."""
+    b = bdist.shard_bounds(counts, world)
+    assert len(b) == world
+    assert b[0][0] == 0 and b[-1][1] == len(counts)
+    assert all(lo <= hi for lo, hi in b)
+    assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    if counts and sum(counts) > 0 and len(counts) >= world:
+        loads = [sum(counts[lo:hi]) for lo, hi in b]
+        assert max(loads) - sum(counts) / world <= max(counts)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.text(min_size=0, max_size=12), min_size=0, max_size=40))
+def test_names_round_trip(names):
+    buf, lens = bdist.pack_names(names)
+    assert buf.dtype == np.uint8 and lens.dtype == np.int32 and int(lens.sum()) == buf.size
+    assert bdist.unpack_names(buf, lens) == [str(n) for n in names]
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(min_value=0, max_value=300), st.sampled_from([np.float32, np.float64]), st.integers(0, 2 ** 31 - 1))
+def test_tile_triples_round_trip_bit_exact(n, dtype, seed):
+    """(pred, unc, label) triples cross ranks as raw bytes: NaN payloads, denormals and -0.0 must survive."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2 ** (8 * np.dtype(dtype).itemsize - 1), n, dtype=np.uint64)
+    yp = bits.astype({4: np.uint32, 8: np.uint64}[np.dtype(dtype).itemsize]).view(dtype)
+    un = rng.standard_normal(n).astype(dtype)
+    yt = rng.integers(0, 2, n).astype(np.uint8)
+    buf = bdist.pack_tiles(yp, un, yt)
+    assert buf.size == n * (2 * np.dtype(dtype).itemsize + 1)
+    a, b, c = bdist.unpack_tiles(buf, n, dtype)
+    assert a.tobytes() == yp.tobytes() and b.tobytes() == un.tobytes() and c.tobytes() == yt.tobytes()
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(min_value=1, max_value=40), st.integers(0, 2 ** 31 - 1))
+def test_group_messages_keep_first_appearance_order(L, seed):
+    """pack_groups / unpack_groups: float32 means are exact in the float64 message, groups with no surviving tile drop
+    out, and the survivors come back ordered by their first surviving ROW (the reference's first-appearance order)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 5, L)
+    first = np.where(counts > 0, rng.permutation(L * 3)[:L], -1)
+    yp, un = rng.random(L).astype(np.float32), rng.random(L).astype(np.float32)
+    yt = rng.integers(0, 2, L).astype(np.float64)
+    msg = bdist.pack_groups(7, counts, first, 100, yp, un, yt)
+    g = bdist.unpack_groups(msg, np.float32)
+    alive = np.nonzero(counts > 0)[0]
+    order = alive[np.argsort(first[alive], kind="stable")]
+    assert list(g["code"]) == list(order + 7)
+    assert g["y_pred"].tobytes() == yp[order].tobytes() and g["uncertainty"].tobytes() == un[order].tobytes()
+    assert list(g["count"]) == list(counts[order]) and list(g["y_true"]) == list(yt[order].astype(np.uint8))
