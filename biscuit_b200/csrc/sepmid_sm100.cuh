@@ -1,5 +1,5 @@
-// Fused SeparableConv2D for the 728 -> 728 layers on the 19 x 19 maps (24 middle-flow layers + block13_sepconv1:
-// 56 % of the network's FLOPs).  The depthwise result never exists in HBM and nothing is computed twice:
+// Fused SeparableConv2D for the 728 -> 728 layers on the 19 x 19 maps (the 24 middle-flow layers: 56 % of the
+// network's FLOPs).  The depthwise result never exists in HBM and nothing is computed twice:
 //
 //     out[p, n] = epilogue( sum_c  depthwise3x3(relu?(x))[p, c] * Wpw[n, c] )        (+ residual[p, n])
 //
@@ -21,22 +21,24 @@
 //     3 x 160 = 480 TMEM columns per CTA, so every depthwise k-block is produced once and used for all 728 outputs.
 //
 // Work item = 160 consecutive padded rows (8 padded image rows) per CTA pair; per 64-channel k-block and CTA:
-//   warp 0        TMA: the (80 + 42)-row input window of this CTA's 80 pixels, and three 128 x 64 weight tiles
+//   warp 0        TMA: the 128 x 64 weight tiles (this CTA's half of each 256-row channel tile), a ring of five single
+//                 tiles in exactly the order the MMAs consume them
+//   warp 14       TMA: the (80 + 42)-row input window of this CTA's 80 pixels (its own warp: behind the weight ring's
+//                 waits the window requests were issued late)
 //   warps 10-13   depthwise producers: thread = 4 channels x (2 image rows x 5 columns); the 4 x 7 halo is read once
 //                 (28 LDS.64 + 180 FFMA2 per 10 outputs, same tap order as depthwise3x3_pipe_kernel) -> bf16 ->
-//                 this CTA's half of the 128B-swizzled N-side stage
+//                 this CTA's half of the 128B-swizzled N-side stage (4 stages)
 //   warp 1        (leader CTA) 3 x 4 tcgen05.mma.cta_group::2 (M = 256, N = 160, K = 16) per k-block
-//   warps 2-9     epilogue per channel tile: tcgen05.ld -> BN scale/shift (per-lane constants: lane = channel)
-//                 (+ residual) (ReLU) -> bf16 -> [pixel][channel] staging -> TMA stores of the VALID pixels only
-//                 (one 19-pixel box per image row), so the zero border is never touched.
+//   warps 2-9     epilogue, eight independent warp pipelines on accumulator fragments: tcgen05.ld.16x256b -> BN
+//                 scale/shift (four constant pairs per thread) (+ residual, fetched by the warp's own TMA load and added
+//                 with FHADD.BF16) -> cvt.rn(.relu) pack -> stmatrix.trans into the warp's [40 px][32 ch] staging tile
+//                 -> TMA stores of the VALID pixels only (one 19-pixel box per image row): the zero border is never touched.
 // The accumulators are single-buffered (480 of 512 columns), so a channel tile cannot take the next item's MMAs before
-// the epilogue has read it.  To keep the tensor pipe busy across item boundaries the three channel tiles are SKEWED by
-// one k-block: in step t the MMA warp issues (tile 0, k-block t), (tile 1, k-block t-1), (tile 2, k-block t-2) of one
-// continuous k-block stream over all items.  Tile 0 finishes an item two steps before tile 2, the three drains happen at
-// different times, and while one tile waits for its drain the other two still have MMAs to run (measured with the
-// tiles in lock-step: 28 % of the kernel was the tensor pipe waiting for the three drains in a row).  A depthwise
-// k-block therefore lives for three steps (4 stages), and the weight ring is a ring of single 128 x 64 tiles in exactly
-// the order the MMAs consume them.
+// the epilogue has read it.  The three channel tiles are SKEWED by one k-block: in step t the MMA warp issues
+// (tile 0, k-block t), (tile 1, k-block t-1), (tile 2, k-block t-2) of one continuous k-block stream over all items, so
+// the three drains fall in different steps and a depthwise k-block lives for three steps.  Measured, the skew alone
+// buys nothing (one in-order issuing thread still queues the runnable tiles behind a waiting one);
+// it is kept as the precondition for per-tile issuers.
 #pragma once
 
 #include "gemm_sm100.cuh"
